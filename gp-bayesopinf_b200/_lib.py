@@ -1,0 +1,267 @@
+"""ctypes binding of ``libgpbo.so`` (C ABI declared in ``include/gpbo.h``).
+
+This is the whole host<->device boundary of the package: plain pointers and sizes, no torch
+types.  There is NO CPU fallback -- if the shared library is missing or no CUDA device is
+present, every compute call raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgpbo.so")
+
+NCLASS = 11
+KERNEL_CLASSES = ("prep", "chol_diag", "chol_panel", "trsv", "trtri", "lauum_grad", "finalize",
+                  "cross_panel", "schur", "mean_std", "assemble")
+
+EXPORTS = (
+    "gpbo_version", "gpbo_last_error", "gpbo_create", "gpbo_destroy", "gpbo_launch_count",
+    "gpbo_wave_capacity", "gpbo_assemble", "gpbo_lml_grad", "gpbo_lml_grad_host", "gpbo_fit_host",
+    "gpbo_predict_host", "gpbo_lstsq_moments_host", "gpbo_lstsq_moments", "gpbo_profile_enable",
+    "gpbo_profile_get", "gpbo_bench_dmma_peak", "gpbo_lbfgsb_minimize",
+)
+
+
+OBJECTIVE_FN = C.CFUNCTYPE(C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p)
+
+
+class GpboError(RuntimeError):
+    """Raised when a libgpbo call returns a non-zero status."""
+
+
+_lib = None
+
+
+def load():
+    """Load libgpbo.so (built by ``__graft_entry__.build()`` / ``csrc/Makefile``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise GpboError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    dp, ip, vp = C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_void_p
+    lib.gpbo_version.restype = C.c_int
+    lib.gpbo_last_error.restype = C.c_char_p
+    lib.gpbo_create.argtypes = [C.POINTER(vp), C.c_int, C.c_size_t]
+    lib.gpbo_destroy.argtypes = [vp]
+    lib.gpbo_launch_count.argtypes = [vp]
+    lib.gpbo_launch_count.restype = C.c_longlong
+    lib.gpbo_wave_capacity.argtypes = [vp, C.c_int]
+    lib.gpbo_assemble.argtypes = [vp, C.c_int, vp, C.c_long, C.c_int, vp, C.c_long, C.c_int, vp, C.c_int, vp, vp]
+    lib.gpbo_lml_grad.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, vp, vp]
+    lib.gpbo_lml_grad_host.argtypes = [vp, dp, dp, C.c_int, C.c_int, dp, ip, C.c_int, dp, dp, ip]
+    lib.gpbo_fit_host.argtypes = [vp, dp, dp, C.c_int, C.c_int, dp, dp, ip, C.c_int, dp, dp, dp, ip, ip, ip,
+                                  C.POINTER(C.c_longlong), ip]
+    lib.gpbo_predict_host.argtypes = [vp, dp, dp, C.c_int, C.c_int, dp, dp, C.c_long, C.c_int, dp, dp, dp, ip]
+    lib.gpbo_lstsq_moments_host.argtypes = [vp, dp, dp, C.c_int, C.c_int, dp, dp, C.c_long, C.c_int, dp, dp, dp, ip]
+    lib.gpbo_lstsq_moments.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, vp, C.c_long, C.c_int, vp, vp, vp, vp, vp]
+    lib.gpbo_profile_enable.argtypes = [vp, C.c_int]
+    lib.gpbo_profile_get.argtypes = [vp, dp, C.POINTER(C.c_longlong)]
+    lib.gpbo_bench_dmma_peak.argtypes = [vp, C.c_int, dp, dp]
+    lib.gpbo_lbfgsb_minimize.argtypes = [OBJECTIVE_FN, vp, dp, dp, dp, dp, dp, ip, ip, ip]
+    for name in EXPORTS:
+        if name not in ("gpbo_last_error", "gpbo_launch_count"):
+            getattr(lib, name).restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        msg = load().gpbo_last_error().decode("utf-8", "replace")
+        raise GpboError(f"{what} failed (status {rc}): {msg}")
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def _f64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+class Context:
+    """Owns one ``gpbo_ctx`` workspace handle on a CUDA device."""
+
+    def __init__(self, device: int = 0, max_workspace_bytes: int = 0):
+        self._lib = load()
+        h = C.c_void_p()
+        _check(self._lib.gpbo_create(C.byref(h), int(device), int(max_workspace_bytes)), "gpbo_create")
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.gpbo_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- bookkeeping -----------------------------------------------------------------
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.gpbo_launch_count(self._h))
+
+    def wave_capacity(self, m: int) -> int:
+        return int(self._lib.gpbo_wave_capacity(self._h, int(m)))
+
+    def profile_enable(self, on=True):
+        _check(self._lib.gpbo_profile_enable(self._h, 1 if on else 0), "gpbo_profile_enable")
+
+    def profile_get(self):
+        ms = np.zeros(NCLASS)
+        n = np.zeros(NCLASS, dtype=np.int64)
+        _check(self._lib.gpbo_profile_get(self._h, _dp(ms), n.ctypes.data_as(C.POINTER(C.c_longlong))),
+               "gpbo_profile_get")
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(KERNEL_CLASSES)}
+
+    def dmma_peak(self, iters=20000):
+        tf, ms = C.c_double(), C.c_double()
+        _check(self._lib.gpbo_bench_dmma_peak(self._h, int(iters), C.byref(tf), C.byref(ms)), "gpbo_bench_dmma_peak")
+        return tf.value, ms.value
+
+    # -- host-pointer entry points ------------------------------------------------------
+    def lml_grad(self, t, y, theta, gp_of=None, with_grad=True):
+        """t, y: (G, m); theta: (B, 3); gp_of: (B,) int or None (B == G). -> lml (B,), grad (B,3), status (B,)."""
+        t, y = _f64(np.atleast_2d(t)), _f64(np.atleast_2d(y))
+        theta = _f64(np.atleast_2d(theta))
+        G, m = t.shape
+        B = theta.shape[0]
+        if y.shape != t.shape or theta.shape[1] != 3:
+            raise ValueError("lml_grad: shape mismatch")
+        gp = None if gp_of is None else np.ascontiguousarray(gp_of, dtype=np.int32)
+        lml = np.empty(B)
+        grad = np.empty((B, 3)) if with_grad else None
+        st = np.empty(B, dtype=np.int32)
+        _check(self._lib.gpbo_lml_grad_host(self._h, _dp(t), _dp(y), G, m, _dp(theta), _ip(gp), B, _dp(lml),
+                                            _dp(grad), _ip(st)), "gpbo_lml_grad_host")
+        return lml, grad, st
+
+    def fit(self, t, y, bounds_log, starts, gp_of=None, opts=None):
+        """Multi-start L-BFGS-B for all (GP, start) pairs in lock-step.
+
+        bounds_log: (3, 2); starts: (B, 3).  Returns dict(theta, fun, nfev, nit, status, evals, rounds)."""
+        t, y = _f64(np.atleast_2d(t)), _f64(np.atleast_2d(y))
+        G, m = t.shape
+        starts = _f64(np.atleast_2d(starts))
+        B = starts.shape[0]
+        bl = _f64(bounds_log, (3, 2))
+        gp = None if gp_of is None else np.ascontiguousarray(gp_of, dtype=np.int32)
+        o = None if opts is None else _f64(opts, (5,))
+        theta = np.empty((B, 3))
+        fun = np.empty(B)
+        nfev = np.empty(B, dtype=np.int32)
+        nit = np.empty(B, dtype=np.int32)
+        st = np.empty(B, dtype=np.int32)
+        evals = C.c_longlong()
+        rounds = C.c_int()
+        _check(self._lib.gpbo_fit_host(self._h, _dp(t), _dp(y), G, m, _dp(bl), _dp(starts), _ip(gp), B, _dp(o),
+                                       _dp(theta), _dp(fun), _ip(nfev), _ip(nit), _ip(st), C.byref(evals),
+                                       C.byref(rounds)), "gpbo_fit_host")
+        return dict(theta=theta, fun=fun, nfev=nfev, nit=nit, status=st, evals=int(evals.value),
+                    rounds=int(rounds.value))
+
+    def _points(self, pts, G):
+        pts = _f64(pts)
+        if pts.ndim == 1:
+            return pts, 0, pts.shape[0]
+        if pts.shape[0] != G:
+            raise ValueError("per-GP evaluation points must have G rows")
+        return pts, pts.shape[1], pts.shape[1]
+
+    def predict(self, t, y, theta, t_star, want_alpha=False):
+        """Posterior mean and std at t_star ((n,) shared or (G, n)).  -> mean, std, alpha|None, status."""
+        t, y = _f64(np.atleast_2d(t)), _f64(np.atleast_2d(y))
+        G, m = t.shape
+        theta = _f64(np.atleast_2d(theta))
+        pts, stride, n = self._points(t_star, G)
+        mean, std = np.empty((G, n)), np.empty((G, n))
+        alpha = np.empty((G, m)) if want_alpha else None
+        st = np.empty(G, dtype=np.int32)
+        _check(self._lib.gpbo_predict_host(self._h, _dp(t), _dp(y), G, m, _dp(theta), _dp(pts), stride, n, _dp(mean),
+                                           _dp(std), _dp(alpha), _ip(st)), "gpbo_predict_host")
+        return mean, std, alpha, st
+
+    def lstsq_moments(self, t, y, theta, t_est, want_cov=True):
+        """state_estimate, ddt_estimate, ddt_covariance at t_est.  -> state, ddt, cov|None, status."""
+        t, y = _f64(np.atleast_2d(t)), _f64(np.atleast_2d(y))
+        G, m = t.shape
+        theta = _f64(np.atleast_2d(theta))
+        pts, stride, n = self._points(t_est, G)
+        state, ddt = np.empty((G, n)), np.empty((G, n))
+        cov = np.empty((G, n, n)) if want_cov else None
+        st = np.empty(G, dtype=np.int32)
+        _check(self._lib.gpbo_lstsq_moments_host(self._h, _dp(t), _dp(y), G, m, _dp(theta), _dp(pts), stride, n,
+                                                 _dp(state), _dp(ddt), _dp(cov), _ip(st)), "gpbo_lstsq_moments_host")
+        return state, ddt, cov, st
+
+    # -- device-pointer entry points (torch tensors are only address carriers) ------------
+    def assemble_device(self, kind, t1_ptr, t1_stride, n1, t2_ptr, t2_stride, n2, theta_ptr, B, out_ptr, stream=0):
+        _check(self._lib.gpbo_assemble(self._h, int(kind), t1_ptr, int(t1_stride), int(n1), t2_ptr, int(t2_stride),
+                                       int(n2), theta_ptr, int(B), out_ptr, stream), "gpbo_assemble")
+
+    def lml_grad_device(self, t_ptr, y_ptr, G, m, theta_ptr, gpof_ptr, B, lml_ptr, grad_ptr, status_ptr, stream=0):
+        _check(self._lib.gpbo_lml_grad(self._h, t_ptr, y_ptr, int(G), int(m), theta_ptr, gpof_ptr, int(B), lml_ptr,
+                                       grad_ptr, status_ptr, stream), "gpbo_lml_grad")
+
+    def lstsq_moments_device(self, t_ptr, y_ptr, G, m, theta_ptr, test_ptr, test_stride, n, state_ptr, ddt_ptr,
+                             cov_ptr, status_ptr, stream=0):
+        _check(self._lib.gpbo_lstsq_moments(self._h, t_ptr, y_ptr, int(G), int(m), theta_ptr, test_ptr,
+                                            int(test_stride), int(n), state_ptr, ddt_ptr, cov_ptr, status_ptr, stream),
+               "gpbo_lstsq_moments")
+
+
+_default_ctx = {}
+
+
+def default_context(device: int | None = None) -> Context:
+    """Process-wide context for `device` (default: LOCAL_RANK or 0)."""
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+def lbfgsb_minimize(func, x0, bounds_log, opts=None):
+    """Host-only run of the library's L-BFGS-B state machine on ``func(x) -> (f, g)`` (3 variables).
+    No CUDA device needed; used by the CPU tests to pin the optimiser against scipy."""
+    lib = load()
+
+    def _cb(xp, gp, _user):
+        x = np.array([xp[0], xp[1], xp[2]])
+        f, g = func(x)
+        for i in range(3):
+            gp[i] = float(g[i])
+        return float(f)
+
+    cb = OBJECTIVE_FN(_cb)
+    x0 = _f64(x0, (3,))
+    bl = _f64(bounds_log, (3, 2))
+    o = None if opts is None else _f64(opts, (5,))
+    x = np.empty(3)
+    f = C.c_double()
+    nfev, nit, st = C.c_int(), C.c_int(), C.c_int()
+    _check(lib.gpbo_lbfgsb_minimize(cb, None, _dp(x0), _dp(bl), _dp(o), _dp(x), C.byref(f), C.byref(nfev),
+                                    C.byref(nit), C.byref(st)), "gpbo_lbfgsb_minimize")
+    return dict(x=x, fun=f.value, nfev=nfev.value, nit=nit.value, status=st.value)

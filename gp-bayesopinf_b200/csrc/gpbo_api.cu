@@ -1,0 +1,685 @@
+// C ABI of libgpbo.so (see include/gpbo.h): workspace handle, wave scheduling over the
+// (GP x start) batch, the lock-step multi-start optimiser driver, and the posterior-moment path.
+#include "../../include/gpbo.h"
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels_predict.cuh"
+#include "lbfgsb.h"
+
+using namespace gpbo;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t e__ = (expr);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return fail(GPBO_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));      \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    cudaError_t ensure(size_t need) {
+        if (need <= bytes) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; bytes = 0;
+        cudaError_t e = cudaMalloc(&p, need);
+        if (e == cudaSuccess) bytes = need;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct ProfRec { int cls; cudaEvent_t e0, e1; };
+
+}  // namespace
+
+struct gpbo_ctx {
+    int device = 0;
+    size_t limit = 0;
+    cudaStream_t stream = nullptr;   // used by the *_host entry points
+    long long launches = 0;
+    bool profiling = false;
+    std::vector<ProfRec> recs;
+    double prof_ms[GPBO_NCLASS] = {0};
+    long long prof_n[GPBO_NCLASS] = {0};
+    // wave workspace
+    DevBuf A, D, DT, ts, z, alpha, pp, logdet, part, status;
+    // per-call device copies of host inputs / outputs
+    DevBuf t_dev, y_dev, ypad, theta_dev, gpof_dev, lml_dev, grad_dev, st_dev;
+    // prediction
+    DevBuf X, trow, tsrc, out1, out2, cov_dev;
+    // pinned staging for the optimiser rounds
+    double* h_theta = nullptr; double* h_lml = nullptr; double* h_grad = nullptr; int* h_gpof = nullptr;
+    size_t h_cap = 0;
+};
+
+namespace {
+
+enum { C_PREP = 0, C_DIAG, C_PANEL, C_TRSV, C_TRTRI, C_LAUUM, C_FINAL, C_CROSS, C_SCHUR, C_MEAN, C_ASM };
+
+template <class F>
+inline void launch(gpbo_ctx* c, int cls, cudaStream_t s, F&& f) {
+    if (c->profiling) {
+        ProfRec r;
+        r.cls = cls;
+        cudaEventCreate(&r.e0);
+        cudaEventCreate(&r.e1);
+        cudaEventRecord(r.e0, s);
+        f();
+        cudaEventRecord(r.e1, s);
+        c->recs.push_back(r);
+    } else {
+        f();
+    }
+    c->launches += 1;
+}
+
+inline int pad_to_tile(int m) { return (m + TB - 1) / TB * TB; }
+
+size_t pair_bytes(int m_pad) {
+    const size_t T = m_pad / TB;
+    const size_t ntiles = T * (T + 1) / 2;
+    return (size_t)m_pad * m_pad * 8 + 2 * T * TB * TB * 8 + 3 * (size_t)m_pad * 8 + T * 8 + ntiles * 32 +
+           sizeof(PairParams) + 16;
+}
+
+int resolve_limit(gpbo_ctx* c) {
+    if (c->limit == 0) {
+        size_t fr = 0, tot = 0;
+        CUDA_TRY(cudaMemGetInfo(&fr, &tot));
+        c->limit = (size_t)(0.8 * (double)fr);
+    }
+    return GPBO_OK;
+}
+
+int wave_capacity(gpbo_ctx* c, int m_pad, size_t extra_per_pair, size_t reserved, int want) {
+    if (resolve_limit(c)) return -1;
+    const size_t per = pair_bytes(m_pad) + extra_per_pair;
+    if (c->limit <= reserved + per) return 0;
+    size_t cap = (c->limit - reserved) / per;
+    if (cap > (size_t)want) cap = want;
+    else if (cap >= 148) cap = cap / 148 * 148;
+    return (int)cap;
+}
+
+int ensure_wave(gpbo_ctx* c, int m_pad, int cap) {
+    const size_t T = m_pad / TB, ntiles = T * (T + 1) / 2;
+    CUDA_TRY(c->A.ensure((size_t)cap * m_pad * m_pad * 8));
+    CUDA_TRY(c->D.ensure((size_t)cap * T * TB * TB * 8));
+    CUDA_TRY(c->DT.ensure((size_t)cap * T * TB * TB * 8));
+    CUDA_TRY(c->ts.ensure((size_t)cap * m_pad * 8));
+    CUDA_TRY(c->z.ensure((size_t)cap * m_pad * 8));
+    CUDA_TRY(c->alpha.ensure((size_t)cap * m_pad * 8));
+    CUDA_TRY(c->pp.ensure((size_t)cap * sizeof(PairParams)));
+    CUDA_TRY(c->logdet.ensure((size_t)cap * T * 8));
+    CUDA_TRY(c->part.ensure((size_t)cap * ntiles * 32));
+    CUDA_TRY(c->status.ensure((size_t)cap * 4));
+    return GPBO_OK;
+}
+
+MatArgs mat_args(gpbo_ctx* c, int m, int m_pad) {
+    MatArgs a;
+    a.A = c->A.as<double>();
+    a.mat_stride = (long)m_pad * m_pad;
+    a.lda = m_pad;
+    a.m = m;
+    a.T = m_pad / TB;
+    a.D = c->D.as<double>();
+    a.DT = c->DT.as<double>();
+    a.logdet = c->logdet.as<double>();
+    a.status = c->status.as<int>();
+    a.pp = c->pp.as<PairParams>();
+    a.ts = c->ts.as<double>();
+    return a;
+}
+
+bool g_attr_done = false;
+int set_kernel_attrs() {
+    if (g_attr_done) return GPBO_OK;
+    CUDA_TRY(cudaFuncSetAttribute(chol_diag_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(chol_diag_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(chol_panel_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(chol_panel_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(chol_panel_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(trsv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(trsv_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(trtri_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(lauum_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
+    g_attr_done = true;
+    return GPBO_OK;
+}
+
+// Factor K(theta) for nb pairs and solve for alpha.  order: 0 sklearn, 1 rbf_eval.
+int factor_wave(gpbo_ctx* c, cudaStream_t s, const MatArgs& a, const double* t_dev, const double* ypad,
+                const double* theta_dev, const int* gpof_dev, int nb, int order) {
+    launch(c, C_PREP, s, [&] {
+        prep_pairs_kernel<<<nb, 256, 0, s>>>(theta_dev, gpof_dev, t_dev, a.m, a.lda, order, c->pp.as<PairParams>(),
+                                             c->ts.as<double>(), c->status.as<int>());
+    });
+    CrossArgs none{nullptr, 0, 0, 0};
+    for (int j = 0; j < a.T; ++j) {
+        launch(c, C_DIAG, s, [&] {
+            if (order == 0) chol_diag_kernel<0><<<nb, NTHR, MAIN_SMEM, s>>>(a, j);
+            else chol_diag_kernel<1><<<nb, NTHR, MAIN_SMEM, s>>>(a, j);
+        });
+        if (j < a.T - 1) {
+            const int grid = nb * (a.T - 1 - j);
+            launch(c, C_PANEL, s, [&] {
+                if (order == 0) chol_panel_kernel<0, false><<<grid, NTHR, TILE_SMEM, s>>>(a, j, nullptr, 0, 0, none);
+                else chol_panel_kernel<1, false><<<grid, NTHR, TILE_SMEM, s>>>(a, j, nullptr, 0, 0, none);
+            });
+        }
+    }
+    launch(c, C_TRSV, s, [&] { trsv_fwd_kernel<<<nb, NTHR, DIAG_SMEM, s>>>(a, ypad, c->z.as<double>()); });
+    launch(c, C_TRSV, s, [&] { trsv_bwd_kernel<<<nb, NTHR, DIAG_SMEM, s>>>(a, c->z.as<double>(), c->alpha.as<double>()); });
+    CUDA_TRY(cudaGetLastError());
+    return GPBO_OK;
+}
+
+int eval_wave(gpbo_ctx* c, cudaStream_t s, const double* t_dev, const double* ypad, int m, int m_pad,
+              const double* theta_dev, const int* gpof_dev, int nb, bool with_grad, double* lml, double* grad,
+              int* status) {
+    MatArgs a = mat_args(c, m, m_pad);
+    int rc = factor_wave(c, s, a, t_dev, ypad, theta_dev, gpof_dev, nb, 0);
+    if (rc) return rc;
+    const int ntiles = a.T * (a.T + 1) / 2;
+    if (with_grad) {
+        for (int i = 1; i < a.T; ++i)
+            launch(c, C_TRTRI, s, [&] { trtri_row_kernel<<<nb * i, NTHR, TILE_SMEM, s>>>(a, i); });
+        launch(c, C_LAUUM, s, [&] {
+            lauum_grad_kernel<<<nb * ntiles, NTHR, MAIN_SMEM, s>>>(a, c->alpha.as<double>(), c->part.as<double>(), ntiles);
+        });
+    }
+    launch(c, C_FINAL, s, [&] {
+        finalize_kernel<<<nb, NTHR, 0, s>>>(a, ypad, c->alpha.as<double>(), c->part.as<double>(), ntiles, lml, grad, status,
+                                            with_grad ? 1 : 0);
+    });
+    CUDA_TRY(cudaGetLastError());
+    return GPBO_OK;
+}
+
+int make_ypad(gpbo_ctx* c, cudaStream_t s, const double* y_dev, int G, int m, int m_pad) {
+    CUDA_TRY(c->ypad.ensure((size_t)G * m_pad * 8));
+    launch(c, C_PREP, s, [&] { pad_rows_kernel<<<G, 256, 0, s>>>(y_dev, m, m_pad, c->ypad.as<double>()); });
+    return GPBO_OK;
+}
+
+// All pairs, in waves.  All pointers are device pointers.
+int lml_grad_device(gpbo_ctx* c, cudaStream_t s, const double* t, const double* y, int G, int m, const double* theta,
+                    const int* gp_of, int B, double* lml, double* grad, int* status) {
+    if (!c || !t || !y || !theta || !lml || G <= 0 || m <= 0 || B < 0) return fail(GPBO_EINVAL, "lml_grad: bad argument");
+    if (B == 0) return GPBO_OK;
+    if (!gp_of) return fail(GPBO_EINVAL, "lml_grad: internal: gp_of must be materialised");
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc = set_kernel_attrs();
+    if (rc) return rc;
+    const int m_pad = pad_to_tile(m);
+    const size_t reserved = (size_t)G * m_pad * 8 + (1 << 20);
+    const int cap = wave_capacity(c, m_pad, 0, reserved, B);
+    if (cap <= 0) return fail(GPBO_ENOMEM, "lml_grad: one pair does not fit the workspace limit");
+    rc = ensure_wave(c, m_pad, cap);
+    if (rc) return rc;
+    rc = make_ypad(c, s, y, G, m, m_pad);
+    if (rc) return rc;
+    for (int w0 = 0; w0 < B; w0 += cap) {
+        const int nb = std::min(cap, B - w0);
+        rc = eval_wave(c, s, t, c->ypad.as<double>(), m, m_pad, theta + 3 * (size_t)w0, gp_of + w0, nb,
+                       grad != nullptr, lml + w0, grad ? grad + 3 * (size_t)w0 : nullptr, status ? status + w0 : nullptr);
+        if (rc) return rc;
+    }
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return GPBO_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int gpbo_version(void) { return 100; }
+const char* gpbo_last_error(void) { return g_err.c_str(); }
+
+int gpbo_create(gpbo_ctx** out, int device, size_t max_workspace_bytes) {
+    if (!out) return fail(GPBO_EINVAL, "gpbo_create: out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(GPBO_ECUDA, std::string("gpbo_create: no CUDA device (") + cudaGetErrorString(e) + ")");
+    if (device < 0 || device >= n) return fail(GPBO_EINVAL, "gpbo_create: bad device index");
+    CUDA_TRY(cudaSetDevice(device));
+    gpbo_ctx* c = new gpbo_ctx();
+    c->device = device;
+    c->limit = max_workspace_bytes;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    *out = c;
+    return GPBO_OK;
+}
+
+int gpbo_destroy(gpbo_ctx* c) {
+    if (!c) return GPBO_OK;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    DevBuf* bufs[] = {&c->A, &c->D, &c->DT, &c->ts, &c->z, &c->alpha, &c->pp, &c->logdet, &c->part, &c->status,
+                      &c->t_dev, &c->y_dev, &c->ypad, &c->theta_dev, &c->gpof_dev, &c->lml_dev, &c->grad_dev, &c->st_dev,
+                      &c->X, &c->trow, &c->tsrc, &c->out1, &c->out2, &c->cov_dev};
+    for (DevBuf* b : bufs) b->release();
+    for (auto& r : c->recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    if (c->h_theta) cudaFreeHost(c->h_theta);
+    if (c->h_lml) cudaFreeHost(c->h_lml);
+    if (c->h_grad) cudaFreeHost(c->h_grad);
+    if (c->h_gpof) cudaFreeHost(c->h_gpof);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return GPBO_OK;
+}
+
+long long gpbo_launch_count(const gpbo_ctx* c) { return c ? c->launches : 0; }
+
+int gpbo_wave_capacity(gpbo_ctx* c, int m) {
+    if (!c || m <= 0) return fail(GPBO_EINVAL, "wave_capacity: bad argument");
+    if (cudaSetDevice(c->device) != cudaSuccess) return fail(GPBO_ECUDA, "cudaSetDevice failed");
+    return wave_capacity(c, pad_to_tile(m), 0, 1 << 20, 1 << 30);
+}
+
+int gpbo_profile_enable(gpbo_ctx* c, int on) {
+    if (!c) return fail(GPBO_EINVAL, "profile_enable: ctx is NULL");
+    for (auto& r : c->recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    c->recs.clear();
+    for (int i = 0; i < GPBO_NCLASS; ++i) { c->prof_ms[i] = 0; c->prof_n[i] = 0; }
+    c->profiling = on != 0;
+    return GPBO_OK;
+}
+
+int gpbo_profile_get(gpbo_ctx* c, double* ms, long long* launches) {
+    if (!c || !ms || !launches) return fail(GPBO_EINVAL, "profile_get: bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    for (auto& r : c->recs) {
+        float f = 0.f;
+        cudaEventElapsedTime(&f, r.e0, r.e1);
+        c->prof_ms[r.cls] += f;
+        c->prof_n[r.cls] += 1;
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    c->recs.clear();
+    for (int i = 0; i < GPBO_NCLASS; ++i) { ms[i] = c->prof_ms[i]; launches[i] = c->prof_n[i]; }
+    return GPBO_OK;
+}
+
+int gpbo_assemble(gpbo_ctx* c, int kind, const double* t1, long t1_stride, int n1, const double* t2, long t2_stride,
+                  int n2, const double* theta, int B, double* out, void* stream) {
+    if (!c || !t1 || !t2 || !theta || !out || n1 <= 0 || n2 <= 0 || B <= 0 || kind < 0 || kind > 6)
+        return fail(GPBO_EINVAL, "assemble: bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    dim3 grid((n2 + 2 * NTHR - 1) / (2 * NTHR), (n1 + ASM_ROWS - 1) / ASM_ROWS, B);
+    launch(c, C_ASM, s, [&] {
+        assemble_kernel<<<grid, NTHR, 0, s>>>(kind, t1, t1_stride, n1, t2, t2_stride, n2, theta, B, out, (long)n1 * n2);
+    });
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return GPBO_OK;
+}
+
+int gpbo_lml_grad(gpbo_ctx* c, const double* t, const double* y, int G, int m, const double* theta, const int* gp_of,
+                  int B, double* lml, double* grad, int* status, void* stream) {
+    if (!c) return fail(GPBO_EINVAL, "lml_grad: ctx is NULL");
+    if (!gp_of && B != G) return fail(GPBO_EINVAL, "lml_grad: gp_of is NULL but B != G");
+    if (!gp_of) {
+        // identity map: materialise it so waves can be sliced uniformly
+        CUDA_TRY(cudaSetDevice(c->device));
+        std::vector<int> id(B);
+        for (int i = 0; i < B; ++i) id[i] = i;
+        CUDA_TRY(c->gpof_dev.ensure((size_t)B * 4));
+        CUDA_TRY(cudaMemcpy(c->gpof_dev.p, id.data(), (size_t)B * 4, cudaMemcpyHostToDevice));
+        gp_of = c->gpof_dev.as<int>();
+    }
+    return lml_grad_device(c, static_cast<cudaStream_t>(stream), t, y, G, m, theta, gp_of, B, lml, grad, status);
+}
+
+static int upload_problem(gpbo_ctx* c, cudaStream_t s, const double* t, const double* y, int G, int m) {
+    CUDA_TRY(c->t_dev.ensure((size_t)G * m * 8));
+    CUDA_TRY(c->y_dev.ensure((size_t)G * m * 8));
+    CUDA_TRY(cudaMemcpyAsync(c->t_dev.p, t, (size_t)G * m * 8, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(c->y_dev.p, y, (size_t)G * m * 8, cudaMemcpyHostToDevice, s));
+    return GPBO_OK;
+}
+
+static int upload_pairs(gpbo_ctx* c, cudaStream_t s, const double* theta, const int* gp_of, int G, int B) {
+    CUDA_TRY(c->theta_dev.ensure((size_t)B * 24));
+    CUDA_TRY(c->gpof_dev.ensure((size_t)B * 4));
+    CUDA_TRY(c->lml_dev.ensure((size_t)B * 8));
+    CUDA_TRY(c->grad_dev.ensure((size_t)B * 24));
+    CUDA_TRY(c->st_dev.ensure((size_t)B * 4));
+    CUDA_TRY(cudaMemcpyAsync(c->theta_dev.p, theta, (size_t)B * 24, cudaMemcpyHostToDevice, s));
+    if (gp_of) {
+        for (int b = 0; b < B; ++b)
+            if (gp_of[b] < 0 || gp_of[b] >= G) return fail(GPBO_EINVAL, "gp_of entry out of range");
+        CUDA_TRY(cudaMemcpyAsync(c->gpof_dev.p, gp_of, (size_t)B * 4, cudaMemcpyHostToDevice, s));
+    } else {
+        std::vector<int> id(B);
+        for (int i = 0; i < B; ++i) id[i] = i;
+        CUDA_TRY(cudaMemcpyAsync(c->gpof_dev.p, id.data(), (size_t)B * 4, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+    }
+    return GPBO_OK;
+}
+
+int gpbo_lml_grad_host(gpbo_ctx* c, const double* t, const double* y, int G, int m, const double* theta,
+                       const int* gp_of, int B, double* lml, double* grad, int* status) {
+    if (!c || !t || !y || !theta || !lml || G <= 0 || m <= 0 || B <= 0)
+        return fail(GPBO_EINVAL, "lml_grad_host: bad argument");
+    if (!gp_of && B != G) return fail(GPBO_EINVAL, "lml_grad_host: gp_of is NULL but B != G");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    int rc = upload_problem(c, s, t, y, G, m);
+    if (rc) return rc;
+    rc = upload_pairs(c, s, theta, gp_of, G, B);
+    if (rc) return rc;
+    rc = lml_grad_device(c, s, c->t_dev.as<double>(), c->y_dev.as<double>(), G, m, c->theta_dev.as<double>(),
+                         c->gpof_dev.as<int>(), B, c->lml_dev.as<double>(), grad ? c->grad_dev.as<double>() : nullptr,
+                         c->st_dev.as<int>());
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(lml, c->lml_dev.p, (size_t)B * 8, cudaMemcpyDeviceToHost, s));
+    if (grad) CUDA_TRY(cudaMemcpyAsync(grad, c->grad_dev.p, (size_t)B * 24, cudaMemcpyDeviceToHost, s));
+    if (status) CUDA_TRY(cudaMemcpyAsync(status, c->st_dev.p, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return GPBO_OK;
+}
+
+int gpbo_fit_host(gpbo_ctx* c, const double* t, const double* y, int G, int m, const double* bounds_log,
+                  const double* starts, const int* gp_of, int B, const double* opts, double* theta_opt, double* fun,
+                  int* nfev, int* nit, int* opt_status, long long* total_evals, int* rounds) {
+    if (!c || !t || !y || !bounds_log || !starts || !theta_opt || !fun || G <= 0 || m <= 0 || B <= 0)
+        return fail(GPBO_EINVAL, "fit_host: bad argument");
+    if (!gp_of && B != G) return fail(GPBO_EINVAL, "fit_host: gp_of is NULL but B != G");
+    for (int i = 0; i < 3; ++i)
+        if (!(bounds_log[2 * i] <= bounds_log[2 * i + 1])) return fail(GPBO_EINVAL, "fit_host: empty bound interval");
+    if (gp_of)
+        for (int b = 0; b < B; ++b)
+            if (gp_of[b] < 0 || gp_of[b] >= G) return fail(GPBO_EINVAL, "fit_host: gp_of entry out of range");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    int rc = upload_problem(c, s, t, y, G, m);
+    if (rc) return rc;
+    if (c->h_cap < (size_t)B) {
+        if (c->h_theta) { cudaFreeHost(c->h_theta); cudaFreeHost(c->h_lml); cudaFreeHost(c->h_grad); cudaFreeHost(c->h_gpof); }
+        CUDA_TRY(cudaMallocHost(&c->h_theta, (size_t)B * 24));
+        CUDA_TRY(cudaMallocHost(&c->h_lml, (size_t)B * 8));
+        CUDA_TRY(cudaMallocHost(&c->h_grad, (size_t)B * 24));
+        CUDA_TRY(cudaMallocHost(&c->h_gpof, (size_t)B * 4));
+        c->h_cap = B;
+    }
+    CUDA_TRY(c->theta_dev.ensure((size_t)B * 24));
+    CUDA_TRY(c->gpof_dev.ensure((size_t)B * 4));
+    CUDA_TRY(c->lml_dev.ensure((size_t)B * 8));
+    CUDA_TRY(c->grad_dev.ensure((size_t)B * 24));
+
+    LbOptions o;
+    if (opts) {
+        o.factr = opts[0]; o.pgtol = opts[1]; o.maxiter = (int)opts[2]; o.maxfun = (int)opts[3]; o.maxls = (int)opts[4];
+    }
+    double lo[3] = {bounds_log[0], bounds_log[2], bounds_log[4]};
+    double hi[3] = {bounds_log[1], bounds_log[3], bounds_log[5]};
+    std::vector<Lbfgsb> opt(B);
+    for (int b = 0; b < B; ++b) opt[b].init(starts + 3 * (size_t)b, lo, hi, o);
+    std::vector<int> live;
+    live.reserve(B);
+    long long evals = 0;
+    int nround = 0;
+    for (;;) {
+        live.clear();
+        for (int b = 0; b < B; ++b)
+            if (opt[b].running()) live.push_back(b);
+        if (live.empty()) break;
+        const int n = (int)live.size();
+        for (int k = 0; k < n; ++k) {
+            const int b = live[k];
+            c->h_theta[3 * k] = opt[b].x[0]; c->h_theta[3 * k + 1] = opt[b].x[1]; c->h_theta[3 * k + 2] = opt[b].x[2];
+            c->h_gpof[k] = gp_of ? gp_of[b] : b;
+        }
+        CUDA_TRY(cudaMemcpyAsync(c->theta_dev.p, c->h_theta, (size_t)n * 24, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(c->gpof_dev.p, c->h_gpof, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+        rc = lml_grad_device(c, s, c->t_dev.as<double>(), c->y_dev.as<double>(), G, m, c->theta_dev.as<double>(),
+                             c->gpof_dev.as<int>(), n, c->lml_dev.as<double>(), c->grad_dev.as<double>(), nullptr);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(c->h_lml, c->lml_dev.p, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(c->h_grad, c->grad_dev.p, (size_t)n * 24, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        for (int k = 0; k < n; ++k) {
+            const int b = live[k];
+            double gneg[3] = {-c->h_grad[3 * k], -c->h_grad[3 * k + 1], -c->h_grad[3 * k + 2]};
+            opt[b].feed(-c->h_lml[k], gneg);   // obj_func = (-lml, -grad), _gpr.py:300-307
+        }
+        evals += n;
+        nround += 1;
+    }
+    for (int b = 0; b < B; ++b) {
+        for (int i = 0; i < 3; ++i) theta_opt[3 * (size_t)b + i] = opt[b].x[i];
+        fun[b] = opt[b].f;
+        if (nfev) nfev[b] = opt[b].nfev;
+        if (nit) nit[b] = opt[b].nit;
+        if (opt_status) opt_status[b] = opt[b].status;
+    }
+    if (total_evals) *total_evals = evals;
+    if (rounds) *rounds = nround;
+    return GPBO_OK;
+}
+
+int gpbo_lbfgsb_minimize(gpbo_objective_fn fn, void* user, const double* x0, const double* bounds_log,
+                         const double* opts, double* x, double* f, int* nfev, int* nit, int* status) {
+    if (!fn || !x0 || !bounds_log || !x || !f) return fail(GPBO_EINVAL, "lbfgsb_minimize: bad argument");
+    LbOptions o;
+    if (opts) {
+        o.factr = opts[0]; o.pgtol = opts[1]; o.maxiter = (int)opts[2]; o.maxfun = (int)opts[3]; o.maxls = (int)opts[4];
+    }
+    double lo[3] = {bounds_log[0], bounds_log[2], bounds_log[4]};
+    double hi[3] = {bounds_log[1], bounds_log[3], bounds_log[5]};
+    Lbfgsb opt;
+    opt.init(x0, lo, hi, o);
+    while (opt.running()) {
+        double g[3];
+        const double fv = fn(opt.x, g, user);
+        opt.feed(fv, g);
+    }
+    for (int i = 0; i < 3; ++i) x[i] = opt.x[i];
+    *f = opt.f;
+    if (nfev) *nfev = opt.nfev;
+    if (nit) *nit = opt.nit;
+    if (status) *status = opt.status;
+    return GPBO_OK;
+}
+
+// Posterior moments for G GPs (pairs == GPs).  mode 0: predict (mean, std; sklearn order);
+// mode 1: lstsq (state, ddt, cov; rbf_eval order).  All pointers device.
+static int moments_device(gpbo_ctx* c, cudaStream_t s, int mode, const double* t, const double* y, int G, int m,
+                          const double* theta, const double* trow_src, long src_stride, int n, double* out1,
+                          double* out2, double* cov, double* alpha_out, int* status) {
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc = set_kernel_attrs();
+    if (rc) return rc;
+    const int m_pad = pad_to_tile(m), n_pad = pad_to_tile(n), xT = n_pad / TB;
+    const bool need_x = (mode == 0) || (cov != nullptr);
+    const size_t extra = (need_x ? (size_t)n_pad * m_pad * 8 : 0) + (size_t)n_pad * 8;
+    const size_t reserved = (size_t)G * m_pad * 8 + (1 << 20);
+    const int cap = wave_capacity(c, m_pad, extra, reserved, G);
+    if (cap <= 0) return fail(GPBO_ENOMEM, "moments: one GP does not fit the workspace limit");
+    rc = ensure_wave(c, m_pad, cap);
+    if (rc) return rc;
+    if (need_x) CUDA_TRY(c->X.ensure((size_t)cap * n_pad * m_pad * 8));
+    CUDA_TRY(c->trow.ensure((size_t)cap * n_pad * 8));
+    CUDA_TRY(c->gpof_dev.ensure((size_t)G * 4));
+    {
+        std::vector<int> id(G);
+        for (int i = 0; i < G; ++i) id[i] = i;
+        CUDA_TRY(cudaMemcpyAsync(c->gpof_dev.p, id.data(), (size_t)G * 4, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+    }
+    rc = make_ypad(c, s, y, G, m, m_pad);
+    if (rc) return rc;
+    const int order = mode == 0 ? 0 : 1;
+    MatArgs a = mat_args(c, m, m_pad);
+    for (int w0 = 0; w0 < G; w0 += cap) {
+        const int nb = std::min(cap, G - w0);
+        rc = factor_wave(c, s, a, t, c->ypad.as<double>(), theta + 3 * (size_t)w0, c->gpof_dev.as<int>() + w0, nb, order);
+        if (rc) return rc;
+        launch(c, C_PREP, s, [&] {
+            scale_rows_kernel<<<nb, 256, 0, s>>>(trow_src + (size_t)w0 * src_stride, src_stride, n, n_pad, order,
+                                                 c->pp.as<PairParams>(), c->trow.as<double>());
+        });
+        CrossArgs cr{c->trow.as<double>(), n, n_pad, mode == 0 ? 0 : 1};
+        dim3 mgrid((n + NTHR / 32 - 1) / (NTHR / 32), nb);
+        launch(c, C_MEAN, s, [&] {
+            mean_kernel<<<mgrid, NTHR, 0, s>>>(a, cr, c->alpha.as<double>(), out1 + (size_t)w0 * n, n);
+        });
+        if (mode == 1) {
+            CrossArgs cr2 = cr;
+            cr2.kind = 2;
+            launch(c, C_MEAN, s, [&] {
+                mean_kernel<<<mgrid, NTHR, 0, s>>>(a, cr2, c->alpha.as<double>(), out2 + (size_t)w0 * n, n);
+            });
+        }
+        if (need_x) {
+            CrossArgs crx = cr;
+            crx.kind = mode == 0 ? 0 : 2;
+            const long xs = (long)n_pad * m_pad;
+            for (int j = 0; j < a.T; ++j)
+                launch(c, C_CROSS, s, [&] {
+                    chol_panel_kernel<0, true><<<nb * xT, NTHR, TILE_SMEM, s>>>(a, j, c->X.as<double>(), xs, xT, crx);
+                });
+            if (mode == 0) {
+                launch(c, C_MEAN, s, [&] {
+                    std_kernel<<<mgrid, NTHR, 0, s>>>(a, c->X.as<double>(), xs, n, out2 + (size_t)w0 * n, n);
+                });
+            } else {
+                const int ntiles = xT * (xT + 1) / 2;
+                launch(c, C_SCHUR, s, [&] {
+                    schur_kernel<<<nb * ntiles, NTHR, MAIN_SMEM, s>>>(a, c->X.as<double>(), xs, crx, ntiles,
+                                                                      cov + (size_t)w0 * n * n, (long)n * n);
+                });
+            }
+        }
+        if (alpha_out)
+            CUDA_TRY(cudaMemcpy2DAsync(alpha_out + (size_t)w0 * m, (size_t)m * 8, c->alpha.p, (size_t)m_pad * 8,
+                                       (size_t)m * 8, nb, cudaMemcpyDeviceToDevice, s));
+        if (status)
+            CUDA_TRY(cudaMemcpyAsync(status + w0, c->status.p, (size_t)nb * 4, cudaMemcpyDeviceToDevice, s));
+        CUDA_TRY(cudaGetLastError());
+    }
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return GPBO_OK;
+}
+
+static int moments_host(gpbo_ctx* c, int mode, const double* t, const double* y, int G, int m, const double* theta,
+                        const double* pts, long pts_stride, int n, double* o1, double* o2, double* cov, double* alpha,
+                        int* status) {
+    if (!c || !t || !y || !theta || !pts || !o1 || !o2 || G <= 0 || m <= 0 || n <= 0)
+        return fail(GPBO_EINVAL, "moments_host: bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    int rc = upload_problem(c, s, t, y, G, m);
+    if (rc) return rc;
+    CUDA_TRY(c->theta_dev.ensure((size_t)G * 24));
+    CUDA_TRY(cudaMemcpyAsync(c->theta_dev.p, theta, (size_t)G * 24, cudaMemcpyHostToDevice, s));
+    const size_t npts = pts_stride == 0 ? (size_t)n : (size_t)G * pts_stride;
+    CUDA_TRY(c->tsrc.ensure(npts * 8));
+    CUDA_TRY(cudaMemcpyAsync(c->tsrc.p, pts, npts * 8, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(c->out1.ensure((size_t)G * n * 8));
+    CUDA_TRY(c->out2.ensure((size_t)G * n * 8));
+    CUDA_TRY(c->st_dev.ensure((size_t)G * 4));
+    if (cov) CUDA_TRY(c->cov_dev.ensure((size_t)G * n * n * 8));
+    if (alpha) CUDA_TRY(c->grad_dev.ensure((size_t)G * m * 8));
+    rc = moments_device(c, s, mode, c->t_dev.as<double>(), c->y_dev.as<double>(), G, m, c->theta_dev.as<double>(),
+                        c->tsrc.as<double>(), pts_stride, n, c->out1.as<double>(), c->out2.as<double>(),
+                        cov ? c->cov_dev.as<double>() : nullptr, alpha ? c->grad_dev.as<double>() : nullptr,
+                        c->st_dev.as<int>());
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(o1, c->out1.p, (size_t)G * n * 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(o2, c->out2.p, (size_t)G * n * 8, cudaMemcpyDeviceToHost, s));
+    if (cov) CUDA_TRY(cudaMemcpyAsync(cov, c->cov_dev.p, (size_t)G * n * n * 8, cudaMemcpyDeviceToHost, s));
+    if (alpha) CUDA_TRY(cudaMemcpyAsync(alpha, c->grad_dev.p, (size_t)G * m * 8, cudaMemcpyDeviceToHost, s));
+    if (status) CUDA_TRY(cudaMemcpyAsync(status, c->st_dev.p, (size_t)G * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return GPBO_OK;
+}
+
+int gpbo_predict_host(gpbo_ctx* c, const double* t, const double* y, int G, int m, const double* theta,
+                      const double* t_star, long tstar_stride, int n_star, double* mean, double* std, double* alpha,
+                      int* status) {
+    return moments_host(c, 0, t, y, G, m, theta, t_star, tstar_stride, n_star, mean, std, nullptr, alpha, status);
+}
+
+int gpbo_lstsq_moments_host(gpbo_ctx* c, const double* t, const double* y, int G, int m, const double* theta,
+                            const double* t_est, long test_stride, int n_est, double* state, double* ddt, double* cov,
+                            int* status) {
+    return moments_host(c, 1, t, y, G, m, theta, t_est, test_stride, n_est, state, ddt, cov, nullptr, status);
+}
+
+int gpbo_lstsq_moments(gpbo_ctx* c, const double* t, const double* y, int G, int m, const double* theta,
+                       const double* t_est, long test_stride, int n_est, double* state, double* ddt, double* cov,
+                       int* status, void* stream) {
+    if (!c || !t || !y || !theta || !t_est || !state || !ddt || G <= 0 || m <= 0 || n_est <= 0)
+        return fail(GPBO_EINVAL, "lstsq_moments: bad argument");
+    return moments_device(c, static_cast<cudaStream_t>(stream), 1, t, y, G, m, theta, t_est, test_stride, n_est, state,
+                          ddt, cov, nullptr, status);
+}
+
+// ---- FP64 tensor-pipe peak: back-to-back independent DMMA chains --------------------------
+__global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double* out) {
+    double acc[16][2];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
+    const double a = 1e-3 * (threadIdx.x & 7), b = 1e-3 * (threadIdx.x & 3);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dmma884(acc[i], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += acc[i][0] + acc[i][1];
+    if (s == 12345.678) out[0] = s;
+}
+
+int gpbo_bench_dmma_peak(gpbo_ctx* c, int iters, double* tflops, double* ms) {
+    if (!c || !tflops || iters <= 0) return fail(GPBO_EINVAL, "bench_dmma_peak: bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, c->device));
+    const int grid = prop.multiProcessorCount * 4;
+    CUDA_TRY(c->out1.ensure(64));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    dmma_peak_kernel<<<grid, 256, 0, c->stream>>>(iters / 8 + 1, c->out1.as<double>());
+    CUDA_TRY(cudaEventRecord(e0, c->stream));
+    dmma_peak_kernel<<<grid, 256, 0, c->stream>>>(iters, c->out1.as<double>());
+    CUDA_TRY(cudaEventRecord(e1, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->launches += 2;
+    float f = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&f, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    const double flops = (double)grid * 8.0 * (double)iters * 16.0 * 512.0;
+    *tflops = flops / (f * 1e-3) / 1e12;
+    if (ms) *ms = f;
+    return GPBO_OK;
+}
+
+}  // extern "C"

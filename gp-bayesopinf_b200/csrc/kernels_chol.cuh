@@ -1,0 +1,524 @@
+// Batched blocked FP64 Cholesky / triangular inverse / fused K^-1-gradient kernels.
+//
+// One launch processes one algorithmic step for EVERY (GP, start) pair of a wave, so the
+// hyper-parameter optimiser's whole batch advances in lock-step (BASELINE.json north_star (2),(3)).
+// Reference arithmetic: sklearn _gpr.py:583-651 (Cholesky, alpha, LML, K^-1, gradient traces).
+//
+// Per pair the workspace holds one m_pad x m_pad row-major buffer:
+//   lower triangle  : L  (K = L L^T), written block column by block column (left-looking)
+//   upper triangle  : U = L^-T (= W^T, W = L^-1), written block row by block row
+//   side buffers    : D_j = inv(L_jj) and DT_j = D_j^T for every 128x128 diagonal block
+// K itself is never materialised: tiles of K(theta) are generated in the epilogue of the
+// kernel that first needs them, and K^-1 = W^T W is consumed tile-by-tile by the gradient
+// reductions (sum_ij (alpha_i alpha_j - K^-1_ij) dK_ij/dtheta) without being written.
+#pragma once
+#include "tile_engine.cuh"
+
+namespace gpbo {
+
+struct MatArgs {
+    double* A;          // [cap][m_pad*lda]
+    long mat_stride;    // doubles between consecutive pairs' matrices
+    int lda;            // = m_pad
+    int m;              // valid size
+    int T;              // m_pad / 128
+    double* D;          // [cap][T][128*128]
+    double* DT;         // [cap][T][128*128]
+    double* logdet;     // [cap][T]   sum_i log L_ii of each diagonal block
+    int* status;        // [cap]      0 ok, 1 = not positive definite
+    const PairParams* pp;   // [cap]
+    const double* ts;   // [cap][m_pad] scaled abscissae t/ell (sklearn order) or raw t (rbf_eval order)
+};
+
+// ---- element generators ("assemblers") ---------------------------------------------------
+// sklearn order (kernels.py:1559-1565, 1279-1292, 1407-1414): x = t/ell, R = exp(-0.5 (xi-xj)^2),
+// diagonal exactly sigma^2 + chi.
+struct AsmSklearn {
+    double sig2, chi;
+    int m;
+    __device__ __forceinline__ double operator()(int r, int c, double xr, double xc) const {
+        if (r >= m || c >= m) return r == c ? 1.0 : 0.0;
+        if (r == c) return sig2 + chi;
+        const double d = xr - xc;
+        return sig2 * exp(-0.5 * (d * d));
+    }
+};
+// rbf_eval order (gpkernels.py:608-609, 639): kappa = sigma^2 exp(-(ti-tj)^2 / (2 ell^2)), + chi on the diagonal.
+struct AsmRbfEval {
+    double sig2, chi, two_ell2;
+    int m;
+    __device__ __forceinline__ double operator()(int r, int c, double tr, double tcn) const {
+        if (r >= m || c >= m) return r == c ? 1.0 : 0.0;
+        if (r == c) return sig2 + chi;
+        const double d = tr - tcn;
+        return sig2 * exp(-(d * d) / two_ell2);
+    }
+};
+
+template <int ORDER>
+struct AsmSelect;
+template <>
+struct AsmSelect<0> {
+    using type = AsmSklearn;
+    static __device__ __forceinline__ type make(const PairParams& q, int m) { return {q.sig2, q.chi, m}; }
+};
+template <>
+struct AsmSelect<1> {
+    using type = AsmRbfEval;
+    static __device__ __forceinline__ type make(const PairParams& q, int m) {
+        return {q.sig2, q.chi, 2 * (q.ell * q.ell), m};
+    }
+};
+
+// ---- prep: natural-unit hyper-parameters and scaled abscissae ------------------------------
+// ORDER 0: ts = t / ell (sklearn divides X by length_scale before pdist, kernels.py:1559);
+// ORDER 1: ts = t.
+__global__ void prep_pairs_kernel(const double* __restrict__ theta, const int* __restrict__ gp_of,
+                                  const double* __restrict__ t, int m, int m_pad, int order,
+                                  PairParams* __restrict__ pp, double* __restrict__ ts, int* __restrict__ status) {
+    const int p = blockIdx.x;
+    const double sig2 = exp(theta[3 * p + 0]);
+    const double ell = exp(theta[3 * p + 1]);
+    const double chi = exp(theta[3 * p + 2]);
+    const int gp = gp_of ? gp_of[p] : p;
+    if (threadIdx.x == 0) {
+        PairParams q;
+        q.sig2 = sig2; q.ell = ell; q.chi = chi; q.inv_ell2 = 1.0 / (ell * ell); q.gp = gp; q.pad = 0;
+        pp[p] = q;
+        status[p] = 0;
+    }
+    const double* tg = t + (long)gp * m;
+    for (int i = threadIdx.x; i < m_pad; i += blockDim.x)
+        ts[(long)p * m_pad + i] = i < m ? (order == 0 ? tg[i] / ell : tg[i]) : 0.0;
+}
+
+// ---- in-shared factorisation of one 128x128 diagonal block -------------------------------
+// P (stride LDP) holds the symmetric block S on entry (lower part used).  On exit the lower part
+// holds L (S = L L^T), the strict upper part holds inv(L)^T, dinv[i] = 1 / L_ii.
+// Returns (to every thread) whether a non-positive pivot was met; *logsum gets sum_i log L_ii.
+__device__ __forceinline__ bool potf2_trtri_smem(double* P, double* dval, double* dinv, double* logsum_out) {
+    const int tid = threadIdx.x;
+    bool bad = false;
+    const int tr = tid >> 4, tcn = tid & 15;
+    for (int j = 0; j < TB; ++j) {
+        __syncthreads();
+        double d = P[j * LDP + j];
+        if (!(d > 0.0)) { bad = true; d = 1.0; }   // same value on every thread
+        if (tid == 0) dval[j] = d;
+        const double invd = 1.0 / d;
+        for (int r = j + 1 + tr; r < TB; r += 16) {
+            const double lr = P[r * LDP + j] * invd;
+            for (int c = j + 1 + tcn; c <= r; c += 16) P[r * LDP + c] -= lr * P[c * LDP + j];
+        }
+    }
+    __syncthreads();
+    // scale columns: L_rc = S_rc / sqrt(d_c), L_cc = sqrt(d_c)
+    if (tid < TB) {
+        const int c = tid;
+        const double s = sqrt(dval[c]);
+        const double is = 1.0 / s;
+        for (int r = c + 1; r < TB; ++r) P[r * LDP + c] *= is;
+        P[c * LDP + c] = s;
+        dinv[c] = is;
+    }
+    __syncthreads();
+    if (tid < 32) {
+        double ls = 0.0;
+        for (int c = tid; c < TB; c += 32) ls += log(P[c * LDP + c]);
+        ls = warp_sum(ls);
+        if (tid == 0) *logsum_out = ls;
+    }
+    // inverse, two threads per column (even / odd k), X[k][c] kept at P[c][k] (k > c)
+    {
+        const int c = tid >> 1, h = tid & 1;
+        double* xrow = P + c * LDP;
+        const double xc = dinv[c];
+        for (int i = c + 1; i < TB; ++i) {
+            const double* Li = P + i * LDP;
+            double s = (h == 0) ? Li[c] * xc : 0.0;
+            for (int k = c + 1 + h; k < i; k += 2) s += Li[k] * xrow[k];
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            if (h == 0) xrow[i] = -s * dinv[i];
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    return bad;
+}
+
+// ---- Cholesky, diagonal tile of block column j ---------------------------------------------
+// S_jj = K_jj - sum_{k<j} L_jk L_jk^T (DMMA);  L_jj = chol(S_jj);  D_j = inv(L_jj).
+template <int ORDER>
+__global__ void __launch_bounds__(NTHR, 1) chol_diag_kernel(MatArgs a, int j) {
+    extern __shared__ __align__(16) double smem[];
+    const ThreadCoord tc;
+    const int p = blockIdx.x;
+    double* Ap = a.A + (long)p * a.mat_stride;
+    const double* rows = Ap + (long)j * TB * a.lda;
+    Acc acc;
+    acc_zero(acc);
+    auto fa = [&](int kt) { return rows + kt * BK; };
+    gemm_nt_loop<true>(acc, fa, a.lda, fa, a.lda, j * (TB / BK), smem, tc);
+
+    double* P = smem;
+    double* dval = smem + TB * LDP;
+    double* dinv = dval + TB;
+    __shared__ double logsum;
+    {
+        const PairParams q = a.pp[p];
+        const auto el = AsmSelect<ORDER>::make(q, a.m);
+        const double* tsp = a.ts + (long)p * a.lda + j * TB;
+        double xr[8], xc[4][2];
+#pragma unroll
+        for (int mi = 0; mi < 8; ++mi) xr[mi] = tsp[tc.row(mi)];
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) { xc[ni][0] = tsp[tc.col(ni, 0)]; xc[ni][1] = tsp[tc.col(ni, 1)]; }
+#pragma unroll
+        for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int r = tc.row(mi), c = tc.col(ni, e);
+                    if (c <= r)
+                        P[r * LDP + c] = el(j * TB + r, j * TB + c, xr[mi], xc[ni][e]) - acc.v[mi][ni][e];
+                }
+    }
+    const bool bad = potf2_trtri_smem(P, dval, dinv, &logsum);
+
+    // write L_jj (lower), D_j = inv(L_jj) and DT_j = D_j^T
+    double* Lout = Ap + (long)j * TB * a.lda + j * TB;
+    double* Dj = a.D + ((long)p * a.T + j) * (TB * TB);
+    double* DTj = a.DT + ((long)p * a.T + j) * (TB * TB);
+    const int c = tc.tid & (TB - 1);
+    for (int r = tc.tid >> 7; r < TB; r += 2) {
+        if (c <= r) Lout[(long)r * a.lda + c] = P[r * LDP + c];
+        Dj[r * TB + c] = c < r ? P[c * LDP + r] : (c == r ? dinv[r] : 0.0);
+        DTj[r * TB + c] = c > r ? P[r * LDP + c] : (c == r ? dinv[r] : 0.0);
+    }
+    if (tc.tid == 0) {
+        a.logdet[(long)p * a.T + j] = logsum;
+        if (bad) a.status[p] = 1;
+    }
+}
+
+// ---- element generators for rows that are NOT training points (prediction rows) -----------
+// Rows are estimation points t'_a, columns training points t_j (gpkernels.py:630-641).
+struct CrossArgs {
+    const double* trow;   // [G][lrow] row abscissae (t_est, or t_est/ell in sklearn order), zero padded
+    int nrow;             // valid rows (m')
+    int lrow;             // padded rows
+    int kind;             // 0: K(t*, t) sklearn order (predict, _gpr.py:446); 1: kappa_zy; 2: K_zy
+};
+
+__device__ __forceinline__ double cross_element(int kind, const PairParams& q, int r, int c, int nrow, int m,
+                                                double xr, double xc) {
+    if (r >= nrow || c >= m) return 0.0;
+    const double d = xr - xc;
+    if (kind == 0) return q.sig2 * exp(-0.5 * (d * d));
+    const double kap = q.sig2 * exp(-(d * d) / (2 * (q.ell * q.ell)));
+    if (kind == 1) return kap;
+    return -d * kap / (q.ell * q.ell);     // gpkernels.py:640
+}
+
+// ---- Cholesky panel / triangular solve with many right-hand sides -------------------------
+// tile (i, j):  X_ij = (S_ij - sum_{k<j} X_ik L_jk^T) * inv(L_jj)^T
+// CROSS == false: X = L itself (rows i > j of the factor), S = K(theta) tile.
+// CROSS == true : X = V^T (rows = prediction points), S = cross-covariance tile; this is the
+//                 TRSM  V = L^-1 K_zy^T  of gpkernels.py:491 / _gpr.py:460 done as a continuation
+//                 of the Cholesky of the joint covariance.
+template <int ORDER, bool CROSS>
+__global__ void __launch_bounds__(NTHR, 1)
+chol_panel_kernel(MatArgs a, int j, double* X, long x_stride, int xT, CrossArgs cr) {
+    extern __shared__ __align__(16) double smem[];
+    const ThreadCoord tc;
+    int p, i;
+    if (CROSS) { p = blockIdx.x / xT; i = blockIdx.x % xT; }
+    else { const int per = a.T - 1 - j; p = blockIdx.x / per; i = j + 1 + blockIdx.x % per; }
+    const double* Ap = a.A + (long)p * a.mat_stride;
+    double* Xp = CROSS ? X + (long)p * x_stride : a.A + (long)p * a.mat_stride;
+    const double* arows = Xp + (long)i * TB * a.lda;
+    const double* brows = Ap + (long)j * TB * a.lda;
+    Acc acc;
+    acc_zero(acc);
+    gemm_nt_loop<false>(acc, [&](int kt) { return arows + kt * BK; }, a.lda,
+                        [&](int kt) { return brows + kt * BK; }, a.lda, j * (TB / BK), smem, tc);
+
+    double* S = smem;
+    double* ring = smem + TB * LDS;
+    {
+        const PairParams q = a.pp[p];
+        double xr[8], xc[4][2];
+        const double* tcol = a.ts + (long)p * a.lda + j * TB;
+        const double* trow = CROSS ? cr.trow + (long)p * cr.lrow + i * TB : a.ts + (long)p * a.lda + i * TB;
+#pragma unroll
+        for (int mi = 0; mi < 8; ++mi) xr[mi] = trow[tc.row(mi)];
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) { xc[ni][0] = tcol[tc.col(ni, 0)]; xc[ni][1] = tcol[tc.col(ni, 1)]; }
+        const auto el = AsmSelect<ORDER>::make(q, a.m);
+#pragma unroll
+        for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int r = i * TB + tc.row(mi), c = j * TB + tc.col(ni, e);
+                    const double kv = CROSS ? cross_element(cr.kind, q, r, c, cr.nrow, a.m, xr[mi], xc[ni][e])
+                                            : el(r, c, xr[mi], xc[ni][e]);
+                    acc.v[mi][ni][e] = kv - acc.v[mi][ni][e];
+                }
+    }
+    acc_to_smem<LDS>(acc, S, tc);
+    Acc out;
+    acc_zero(out);
+    const double* Dj = a.D + ((long)p * a.T + j) * (TB * TB);
+    epi_product_SxDt(out, S, Dj, ring, tc);
+    double* dst = Xp + (long)i * TB * a.lda + j * TB;
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+            double2 v = make_double2(out.v[mi][ni][0], out.v[mi][ni][1]);
+            *reinterpret_cast<double2*>(dst + (long)tc.row(mi) * a.lda + tc.col(ni, 0)) = v;
+        }
+}
+
+// ---- forward / backward substitution with the block factor ------------------------------
+// z = L^-1 y (one CTA per pair).  _gpr.py:601 (cho_solve, first half).
+__global__ void __launch_bounds__(NTHR, 1) trsv_fwd_kernel(MatArgs a, const double* __restrict__ ypad, double* z) {
+    extern __shared__ __align__(16) double smem[];
+    double* Lb = smem;                 // 128 x LDP
+    double* xs = smem + TB * LDP;      // 128
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int p = blockIdx.x;
+    const double* Ap = a.A + (long)p * a.mat_stride;
+    const double* yp = ypad + (long)a.pp[p].gp * a.lda;
+    double* zp = z + (long)p * a.lda;
+    for (int jb = 0; jb < a.T; ++jb) {
+        const double* rows = Ap + (long)jb * TB * a.lda;
+        const int nk = jb * TB;
+        // r = y_j - L[j, 0:nk] z[0:nk]; 16 rows per warp, lanes across k
+        for (int rr = 0; rr < 16; ++rr) {
+            const int r = warp * 16 + rr;
+            const double* Lr = rows + (long)r * a.lda;
+            double s = 0.0;
+            for (int k = 2 * lane; k < nk; k += 64) {
+                const double2 l = *reinterpret_cast<const double2*>(Lr + k);
+                const double2 zz = *reinterpret_cast<const double2*>(zp + k);
+                s += l.x * zz.x + l.y * zz.y;
+            }
+            s = warp_sum(s);
+            if (lane == 0) xs[r] = yp[jb * TB + r] - s;
+        }
+        // stage L_jj (lower part)
+        for (int q = tid; q < TB * TB; q += NTHR) {
+            const int r = q >> 7, c = q & 127;
+            if (c <= r) Lb[r * LDP + c] = rows[(long)r * a.lda + jb * TB + c];
+        }
+        __syncthreads();
+        if (tid < TB) {
+            double rk = xs[tid];
+            for (int i = 0; i < TB; ++i) {
+                if (tid == i) xs[i] = rk / Lb[i * LDP + i];
+                asm volatile("bar.sync 1, 128;\n" ::);
+                if (tid > i) rk -= Lb[tid * LDP + i] * xs[i];
+            }
+            zp[jb * TB + tid] = xs[tid];
+        }
+        __syncthreads();
+    }
+}
+
+// alpha = L^-T z (one CTA per pair).  _gpr.py:601 (cho_solve, second half).
+__global__ void __launch_bounds__(NTHR, 1) trsv_bwd_kernel(MatArgs a, const double* __restrict__ z, double* alpha) {
+    extern __shared__ __align__(16) double smem[];
+    double* Lb = smem;
+    double* xs = smem + TB * LDP;
+    const int tid = threadIdx.x;
+    const int p = blockIdx.x;
+    const double* Ap = a.A + (long)p * a.mat_stride;
+    const double* zp = z + (long)p * a.lda;
+    double* wp = alpha + (long)p * a.lda;
+    for (int k = tid; k < a.lda; k += NTHR) wp[k] = zp[k];
+    __syncthreads();
+    for (int jb = a.T - 1; jb >= 0; --jb) {
+        const double* rows = Ap + (long)jb * TB * a.lda;
+        for (int q = tid; q < TB * TB; q += NTHR) {
+            const int r = q >> 7, c = q & 127;
+            if (c <= r) Lb[r * LDP + c] = rows[(long)r * a.lda + jb * TB + c];
+        }
+        __syncthreads();
+        if (tid < TB) {
+            double wk = wp[jb * TB + tid];
+            for (int i = TB - 1; i >= 0; --i) {
+                if (tid == i) xs[i] = wk / Lb[i * LDP + i];
+                asm volatile("bar.sync 1, 128;\n" ::);
+                if (tid < i) wk -= Lb[i * LDP + tid] * xs[i];
+            }
+            wp[jb * TB + tid] = xs[tid];
+        }
+        __syncthreads();
+        // w[0:nk] -= L[j, 0:nk]^T alpha_j ; threads across k (coalesced rows)
+        const int nk = jb * TB;
+        for (int k = tid; k < nk; k += NTHR) {
+            double s = 0.0;
+#pragma unroll 8
+            for (int r = 0; r < TB; ++r) s += rows[(long)r * a.lda + k] * xs[r];
+            wp[k] -= s;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- triangular inverse, block row i:  W_ij = -inv(L_ii) sum_{k=j}^{i-1} L_ik W_kj -----------
+// stored transposed: U[j-block rows][i-block cols] = W_ij^T (upper triangle of the pair's buffer).
+__global__ void __launch_bounds__(NTHR, 1) trtri_row_kernel(MatArgs a, int i) {
+    extern __shared__ __align__(16) double smem[];
+    const ThreadCoord tc;
+    const int p = blockIdx.x / i, j = blockIdx.x % i;
+    double* Ap = a.A + (long)p * a.mat_stride;
+    const double* Lrow = Ap + (long)i * TB * a.lda;          // L[i-block rows][*]
+    const double* Urow = Ap + (long)j * TB * a.lda;          // U[j-block rows][*]
+    const double* DTj = a.DT + ((long)p * a.T + j) * (TB * TB);
+    Acc acc;
+    acc_zero(acc);
+    // k-block j: B[n][k] = W_jj[k][n] = DT_j[n][k]
+    gemm_nt_loop<false>(acc, [&](int kt) { return Lrow + j * TB + kt * BK; }, a.lda,
+                        [&](int kt) { return DTj + kt * BK; }, TB, TB / BK, smem, tc);
+    // k-blocks j+1 .. i-1: B[n][k] = U[j*128+n][k]
+    gemm_nt_loop<false>(acc, [&](int kt) { return Lrow + (j + 1) * TB + kt * BK; }, a.lda,
+                        [&](int kt) { return Urow + (j + 1) * TB + kt * BK; }, a.lda, (i - j - 1) * (TB / BK), smem, tc);
+    double* G = smem;
+    double* ring = smem + TB * LDS;
+    acc_to_smem<LDS>(acc, G, tc);      // G[k][n]
+    Acc out;
+    acc_zero(out);
+    const double* Di = a.D + ((long)p * a.T + i) * (TB * TB);
+    epi_product_DxG(out, Di, G, ring, tc);
+    // transposed store: U[j*128 + col][i*128 + row] = -out[row][col]
+    double* dst = Ap + (long)j * TB * a.lda + i * TB;
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) dst[(long)tc.col(ni, e) * a.lda + tc.row(mi)] = -out.v[mi][ni][e];
+}
+
+// ---- fused K^-1 tiles + gradient trace reductions -------------------------------------------
+// tile (I, J), I >= J:  Kinv_IJ = sum_{k >= I} U[I][k] U[J][k]^T  (= (W^T W)_IJ), never stored.
+// Reductions (sklearn _gpr.py:629-651 with kernels.py:1575-1577, 966-969, 1407-1414):
+//   s0 = sum_ij (a_i a_j - Kinv_ij) sigma^2 R_ij
+//   s1 = sum_ij (a_i a_j - Kinv_ij) sigma^2 R_ij (x_i - x_j)^2
+//   s2 = sum_i  (a_i^2   - Kinv_ii)
+// Off-diagonal tiles are counted twice (symmetry).  part[p][tile][4].
+__global__ void __launch_bounds__(NTHR, 1)
+lauum_grad_kernel(MatArgs a, const double* __restrict__ alpha, double* __restrict__ part, int ntiles) {
+    extern __shared__ __align__(16) double smem[];
+    const ThreadCoord tc;
+    const int p = blockIdx.x / ntiles, q = blockIdx.x % ntiles;
+    int I = (int)((sqrt(8.0 * q + 1.0) - 1.0) * 0.5);
+    while ((I + 1) * (I + 2) / 2 <= q) ++I;
+    while (I * (I + 1) / 2 > q) --I;
+    const int J = q - I * (I + 1) / 2;
+    const double* Ap = a.A + (long)p * a.mat_stride;
+    const double* UI = Ap + (long)I * TB * a.lda;
+    const double* UJ = Ap + (long)J * TB * a.lda;
+    const double* DTI = a.DT + ((long)p * a.T + I) * (TB * TB);
+    Acc acc;
+    acc_zero(acc);
+    if (I == J) {
+        gemm_nt_loop<true>(acc, [&](int kt) { return DTI + kt * BK; }, TB, [&](int kt) { return DTI + kt * BK; }, TB,
+                           TB / BK, smem, tc);
+        auto f = [&](int kt) { return UI + (I + 1) * TB + kt * BK; };
+        gemm_nt_loop<true>(acc, f, a.lda, f, a.lda, (a.T - 1 - I) * (TB / BK), smem, tc);
+    } else {
+        gemm_nt_loop<false>(acc, [&](int kt) { return DTI + kt * BK; }, TB,
+                            [&](int kt) { return UJ + I * TB + kt * BK; }, a.lda, TB / BK, smem, tc);
+        gemm_nt_loop<false>(acc, [&](int kt) { return UI + (I + 1) * TB + kt * BK; }, a.lda,
+                            [&](int kt) { return UJ + (I + 1) * TB + kt * BK; }, a.lda, (a.T - 1 - I) * (TB / BK),
+                            smem, tc);
+    }
+    const PairParams pr = a.pp[p];
+    const double* tsp = a.ts + (long)p * a.lda;
+    const double* al = alpha + (long)p * a.lda;
+    double xr[8], ar[8], xc[4][2], ac[4][2];
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi) { xr[mi] = tsp[I * TB + tc.row(mi)]; ar[mi] = al[I * TB + tc.row(mi)]; }
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) { xc[ni][e] = tsp[J * TB + tc.col(ni, e)]; ac[ni][e] = al[J * TB + tc.col(ni, e)]; }
+    double s[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int r = I * TB + tc.row(mi), c = J * TB + tc.col(ni, e);
+                if (r < a.m && c < a.m) {
+                    const double w = ar[mi] * ac[ni][e] - acc.v[mi][ni][e];
+                    if (r == c) {
+                        s[0] += w * pr.sig2;
+                        s[2] += w;
+                    } else {
+                        const double d = xr[mi] - xc[ni][e];
+                        const double d2 = d * d;
+                        const double kr = pr.sig2 * exp(-0.5 * d2);
+                        s[0] += w * kr;
+                        s[1] += w * (kr * d2);
+                    }
+                }
+            }
+    double tot[3];
+    block_sum<3>(s, smem, tot);
+    if (tc.tid == 0) {
+        const double f = (I == J) ? 1.0 : 2.0;
+        double* o = part + ((long)p * ntiles + q) * 4;
+        o[0] = f * tot[0]; o[1] = f * tot[1]; o[2] = tot[2]; o[3] = 0.0;
+    }
+}
+
+// ---- finalize: LML and gradient from the partial sums (one CTA per pair) ---------------------
+// LML = -1/2 y'alpha - sum log L_ii - m/2 log 2pi (_gpr.py:613-617); grad = 1/2 (s0, s1, chi s2).
+__global__ void __launch_bounds__(NTHR, 1)
+finalize_kernel(MatArgs a, const double* __restrict__ ypad, const double* __restrict__ alpha,
+                const double* __restrict__ part, int ntiles, double* __restrict__ lml, double* __restrict__ grad,
+                int* __restrict__ status_out, int with_grad) {
+    __shared__ double red[32];
+    const int p = blockIdx.x, tid = threadIdx.x;
+    const PairParams pr = a.pp[p];
+    const double* yp = ypad + (long)pr.gp * a.lda;
+    const double* al = alpha + (long)p * a.lda;
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int k = tid; k < a.m; k += NTHR) v[0] += yp[k] * al[k];
+    if (with_grad)
+        for (int q = tid; q < ntiles; q += NTHR) {
+            const double* o = part + ((long)p * ntiles + q) * 4;
+            v[1] += o[0]; v[2] += o[1]; v[3] += o[2];
+        }
+    double tot[4];
+    block_sum<4>(v, red, tot);
+    if (tid == 0) {
+        double ld = 0.0;
+        for (int j = 0; j < a.T; ++j) ld += a.logdet[(long)p * a.T + j];
+        const int st = a.status[p];
+        const double val = -0.5 * tot[0] - ld - 0.5 * a.m * 1.8378770664093453;  // log(2 pi)
+        const bool ok = (st == 0) && isfinite(val);
+        lml[p] = ok ? val : -INFINITY;
+        if (with_grad) {
+            grad[3 * p + 0] = ok ? 0.5 * tot[1] : 0.0;
+            grad[3 * p + 1] = ok ? 0.5 * tot[2] : 0.0;
+            grad[3 * p + 2] = ok ? 0.5 * pr.chi * tot[3] : 0.0;
+        }
+        if (status_out) status_out[p] = ok ? 0 : 1;
+    }
+}
+
+__global__ void pad_rows_kernel(const double* __restrict__ src, int n, int n_pad, double* __restrict__ dst) {
+    const int g = blockIdx.x;
+    for (int i = threadIdx.x; i < n_pad; i += blockDim.x) dst[(long)g * n_pad + i] = i < n ? src[(long)g * n + i] : 0.0;
+}
+
+}  // namespace gpbo

@@ -1,0 +1,288 @@
+"""Drop-in replacement for the reference's ``codebase/gpkernels.py`` sklearn path (``GP_RBFW``).
+
+Same constructor, methods, attributes, exceptions and ``str()`` format as the reference
+(``gpkernels.py:299-649``); the arithmetic runs in ``libgpbo.so`` (hand-written sm_100a CUDA) through
+the ctypes layer in ``_lib.py``.  Results surfaced to callers are host NumPy float64 arrays and the
+object stays picklable (``save``/``load`` via joblib, ``gpkernels.py:423-430``).
+
+Not re-implemented here (out of the hot path): the float32 gpytorch variant
+``TORCH_GP_RBFW`` (``gpkernels.py:32-297``).
+
+``sqrtW`` note (SURVEY.md §8a scope note): the GPU computes ``state_estimate``, ``ddt_estimate`` and
+``ddt_covariance``; ``sqrtW = (C + eta I)^(-1/2)`` is then formed on the host from the returned
+covariance with the reference's own formula (``gpkernels.py:496-504``).  It is an API-completeness
+shim outside the four north-star subsystems, excluded from all GPU timings ("next" row N1).
+"""
+
+from __future__ import annotations
+
+import warnings
+
+import numpy as np
+
+from . import _lib
+
+__all__ = ["GP_RBFW", "ConvergenceWarning"]
+
+
+class ConvergenceWarning(UserWarning):
+    """Optimum close to a bound / optimiser did not converge (sklearn emits the same class name)."""
+
+
+# ---- tiny stand-ins for the sklearn objects whose attributes the reference reads --------------
+class _Const:
+    def __init__(self, v):
+        self.constant_value = v
+
+
+class _Rbf:
+    def __init__(self, v):
+        self.length_scale = v
+
+
+class _White:
+    def __init__(self, v):
+        self.noise_level = v
+
+
+class _Prod:
+    def __init__(self, k1, k2):
+        self.k1, self.k2 = k1, k2
+
+
+class _KernelState:
+    """Mirror of sklearn's fitted ``kernel_`` for (C * RBF) + White: ``theta``, ``bounds``, ``k1.k1`` ..."""
+
+    def __init__(self, theta, bounds_log):
+        self.bounds = np.array(bounds_log, dtype=np.float64)
+        self.theta = theta
+
+    @property
+    def theta(self):
+        return self._theta
+
+    @theta.setter
+    def theta(self, th):
+        th = np.array(th, dtype=np.float64)
+        self._theta = th
+        s2, ell, chi = np.exp(th)
+        self.k1 = _Prod(_Const(float(s2)), _Rbf(float(ell)))
+        self.k2 = _White(float(chi))
+
+    def __repr__(self):
+        return (f"{np.sqrt(self.k1.k1.constant_value):.3g}**2 * RBF(length_scale={self.k1.k2.length_scale:.3g})"
+                f" + WhiteKernel(noise_level={self.k2.noise_level:.3g})")
+
+
+class _GPRState:
+    """What the reference exposes through ``gp.gpr`` after ``fit`` (sklearn attribute names)."""
+
+    def __init__(self, bounds_log, n_restarts_optimizer):
+        self.n_restarts_optimizer = int(n_restarts_optimizer)
+        self.alpha = 0
+        self.bounds_log = np.array(bounds_log, dtype=np.float64)
+        self.kernel_ = None
+        self._ctx_device = None
+
+    def log_marginal_likelihood(self, theta=None, eval_gradient=False):
+        """GPU evaluation of sklearn's ``log_marginal_likelihood`` (_gpr.py:541-656)."""
+        if theta is None:
+            return self.log_marginal_likelihood_value_
+        ctx = _lib.default_context(self._ctx_device)
+        lml, grad, _ = ctx.lml_grad(self.X_train_[:, 0][None, :], self.y_train_[None, :],
+                                    np.asarray(theta, dtype=np.float64)[None, :])
+        if eval_gradient:
+            return float(lml[0]), grad[0]
+        return float(lml[0])
+
+
+def _check_bounds(theta, bounds_log, names=("k1__k1__constant_value", "k1__k2__length_scale", "k2__noise_level")):
+    """sklearn kernels.py:436-465: warn when the optimum sits on a bound."""
+    for i, name in enumerate(names):
+        lo, hi = np.exp(bounds_log[i])
+        v = np.exp(theta[i])
+        if np.isclose(theta[i], bounds_log[i, 0], atol=1e-12, rtol=0) or np.isclose(v, lo):
+            warnings.warn(f"The optimal value found for dimension 0 of parameter {name} is close to the specified "
+                          f"lower bound {lo}. Decreasing the bound and calling fit again may find a better value.",
+                          ConvergenceWarning)
+        elif np.isclose(v, hi):
+            warnings.warn(f"The optimal value found for dimension 0 of parameter {name} is close to the specified "
+                          f"upper bound {hi}. Increasing the bound and calling fit again may find a better value.",
+                          ConvergenceWarning)
+
+
+def draw_restart_points(bounds_log, n_restarts):
+    """Restart points exactly as sklearn draws them (_gpr.py:251, 330): ``n_restarts`` calls of
+    ``uniform(log lo, log hi)`` on the GLOBAL NumPy RandomState (SURVEY.md §8b RNG contract)."""
+    rng = np.random.mtrand._rand
+    b = np.asarray(bounds_log, dtype=np.float64)
+    return np.array([rng.uniform(b[:, 0], b[:, 1]) for _ in range(int(n_restarts))]).reshape(-1, 3)
+
+
+def host_sqrtW(C, eta):
+    """``gpkernels.py:496-504`` on the host (shim, see module docstring)."""
+    ev, V = np.linalg.eigh(C + (eta * np.eye(C.shape[0])))
+    if np.any(ev <= 0):
+        raise ValueError("inverse covariance not positive definite, increase eta")
+    return V @ np.diag(1 / np.sqrt(ev)) @ V.T
+
+
+class GP_RBFW:
+    """Gaussian process regressor with kernel  sigma^2 exp(-(t-t')^2 / (2 ell^2)) + chi delta(t,t').
+
+    Mirrors ``gpkernels.GP_RBFW`` (``gpkernels.py:507-649``) and ``_BaseGP`` (``:299-504``).
+    """
+
+    def __init__(self, constant_bounds=(1e-5, 1e5), length_scale_bounds=(1.5e-6, 0.002),
+                 noise_level_bounds=(1e-14, 1e-10), n_restarts_optimizer=50):
+        bounds = np.array([constant_bounds, length_scale_bounds, noise_level_bounds], dtype=np.float64)
+        self.gpr = _GPRState(np.log(bounds), n_restarts_optimizer)
+
+    # Properties ----------------------------------------------------------------
+    @property
+    def nsamples(self):
+        if hasattr(self, "train_indices"):
+            return self.t_training.size
+
+    @property
+    def constant(self):
+        return self.gpr.kernel_.k1.k1.constant_value
+
+    @property
+    def length_scale(self):
+        return self.gpr.kernel_.k1.k2.length_scale
+
+    @property
+    def noise_level(self):
+        return self.gpr.kernel_.k2.noise_level
+
+    def __str__(self):
+        return "\n\t".join([
+            "Gaussian radial basis function kernel",
+            r"k(t, t') = \sigma^2 exp(-(t - t')^2 / (2 \ell^2)) + \chi I",
+            rf"\sigma^2 = {self.constant:.4e}",
+            rf"\ell = {self.length_scale:.4e}",
+            rf"\chi = {self.noise_level:.4e}",
+        ])
+
+    # Main routines -----------------------------------------------------------------
+    def fit(self, t_training, training_data):
+        """Multi-restart maximisation of the log-marginal likelihood (gpkernels.py:330-348 ->
+        sklearn _gpr.py:233-368): start 0 at theta = log(1, 1, 1), then ``n_restarts_optimizer``
+        starts drawn from the global NumPy RNG; all starts advance in lock-step on the GPU."""
+        training_data = np.asarray(training_data)
+        if training_data.ndim > 1:
+            raise ValueError("GP training data must be one-dimensional")
+        t_training = np.asarray(t_training, dtype=np.float64)
+        starts = np.vstack([np.zeros((1, 3)), draw_restart_points(self.gpr.bounds_log, self.gpr.n_restarts_optimizer)])
+        ctx = _lib.default_context()
+        res = ctx.fit(t_training[None, :], training_data[None, :], self.gpr.bounds_log, starts,
+                      gp_of=np.zeros(len(starts), dtype=np.int32))
+        self._set_fit_result(t_training, training_data, res["theta"], res["fun"], res["status"])
+        self._finish_fit(ctx)
+        return self
+
+    def _set_fit_result(self, t_training, training_data, thetas, funs, statuses):
+        self.t_training = t_training
+        self.y = training_data
+        funs = np.where(np.isnan(funs), np.inf, funs)
+        best = int(np.argmin(funs))                      # _gpr.py:336-337
+        theta = thetas[best]
+        self.gpr.kernel_ = _KernelState(theta, self.gpr.bounds_log)
+        _check_bounds(theta, self.gpr.bounds_log)        # _gpr.py:338
+        self.gpr.log_marginal_likelihood_value_ = -float(funs[best])
+        self.gpr.X_train_ = np.array(t_training, dtype=np.float64)[:, None]
+        self.gpr.y_train_ = np.array(training_data, dtype=np.float64)
+        if np.any(statuses[best:best + 1] == 2):
+            warnings.warn("lbfgs failed to converge (abnormal termination in line search).", ConvergenceWarning)
+
+    def _finish_fit(self, ctx, alpha=None, status=None):
+        """alpha_ = K^-1 y at the selected theta (_gpr.py:349-367); non-PD -> LinAlgError."""
+        if alpha is None:
+            _, _, alpha, status = ctx.predict(self.t_training[None, :], self.y[None, :], self.gpr.kernel_.theta[None, :],
+                                              self.t_training[:1], want_alpha=True)
+            alpha, status = alpha[0], status[0]
+        if status != 0:
+            raise np.linalg.LinAlgError(
+                f"The kernel, {self.gpr.kernel_}, is not returning a positive definite matrix. Try gradually "
+                "increasing the 'alpha' parameter of your GaussianProcessRegressor estimator.")
+        self.gpr.alpha_ = alpha
+
+    def predict(self, t):
+        """(mean, std) of the posterior at ``t`` (gpkernels.py:350-365 -> _gpr.py:444-500)."""
+        t = np.asarray(t, dtype=np.float64)
+        ctx = _lib.default_context()
+        mean, std, _, st = ctx.predict(self.t_training[None, :], self.y[None, :], self.gpr.kernel_.theta[None, :], t)
+        if st[0] != 0:
+            raise np.linalg.LinAlgError("kernel matrix not positive definite")
+        if np.any(std[0] == 0.0):
+            warnings.warn("Predicted variances smaller than 0. Setting those variances to 0.")
+        return mean[0], std[0]
+
+    def prediction_bounds(self, t, kind="95%"):
+        mean, std = self.predict(t)
+        if kind == "std":
+            width = std
+        elif kind == "95%":
+            width = 1.96 * std
+        elif kind == "2std":
+            width = 2 * std
+        elif kind == "3std":
+            width = 3 * std
+        else:
+            raise ValueError(kind)
+        return mean - width, mean, mean + width
+
+    def _assemble(self, kind, t1, t2):
+        import torch  # tensor hand-off only
+
+        ctx = _lib.default_context()
+        dev = torch.device("cuda", ctx.device)
+        a = torch.as_tensor(np.ascontiguousarray(t1, dtype=np.float64), device=dev)
+        b = torch.as_tensor(np.ascontiguousarray(t2, dtype=np.float64), device=dev)
+        th = torch.as_tensor(self.gpr.kernel_.theta, device=dev)
+        out = torch.empty((a.numel(), b.numel()), dtype=torch.float64, device=dev)
+        torch.cuda.synchronize(dev)
+        ctx.assemble_device(kind, a.data_ptr(), 0, a.numel(), b.data_ptr(), 0, b.numel(), th.data_ptr(), 1,
+                            out.data_ptr(), 0)
+        return out.cpu().numpy()
+
+    def __call__(self, t, tprime):
+        """kernel_(t, t') = sigma^2 R(t, t') (no white-noise term; gpkernels.py:405-420)."""
+        return self._assemble(2, t, tprime)
+
+    def rbf_eval(self, t1, t2):
+        """kappa(t1, t2) (gpkernels.py:591-609)."""
+        return self._assemble(3, t1, t2)
+
+    # Persistence -----------------------------------------------------------------
+    def save(self, save_path):
+        import joblib
+
+        joblib.dump(self, save_path)
+
+    @staticmethod
+    def load(load_path):
+        import joblib
+
+        return joblib.load(load_path)
+
+    # Least-squares data ---------------------------------------------------------------
+    def compute_lstsq_matrices(self, t_est, eta=1e-8):
+        """state_estimate, ddt_estimate, ddt_covariance, sqrtW at ``t_est`` (gpkernels.py:612-649, 445-504)."""
+        t_est = np.asarray(t_est, dtype=np.float64)
+        ctx = _lib.default_context()
+        state, ddt, cov, st = ctx.lstsq_moments(self.t_training[None, :], self.y[None, :],
+                                                self.gpr.kernel_.theta[None, :], t_est)
+        self._set_lstsq_result(t_est, state[0], ddt[0], cov[0], int(st[0]), eta)
+        return None
+
+    def _set_lstsq_result(self, t_est, state, ddt, cov, status, eta):
+        self.t_estimation = t_est
+        if status != 0 or not np.all(np.isfinite(cov)):
+            # scipy.linalg.cho_factor(K_yy, check_finite=True) raises for the same inputs (gpkernels.py:481)
+            raise np.linalg.LinAlgError("K_yy is not positive definite")
+        self.state_estimate = state
+        self.ddt_estimate = ddt
+        self.ddt_covariance = cov
+        self.sqrtW = host_sqrtW(cov, eta)

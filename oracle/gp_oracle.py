@@ -1,0 +1,244 @@
+"""CPU oracle for the step2_fitgps hot path  --  TEST INFRASTRUCTURE ONLY.
+
+This module is the *checker*, never the product: only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl
+reference`` legs may import it.  Nothing under ``gp-bayesopinf_b200/`` imports
+it, and the product path raises when its CUDA library is missing.
+
+Two independent restatements of the reference algorithm live here:
+
+* ``np_*`` functions: plain NumPy/SciPy-LAPACK formulas, each citing the
+  reference (``/root/reference/codebase/gpkernels.py``) or the third-party code
+  the reference delegates to (scikit-learn ``gaussian_process/_gpr.py`` /
+  ``kernels.py``; pinned by the reference at scikit-learn==1.5.2,
+  scipy==1.14.1, numpy==2.1.3 -- ``requirements.txt:4-7``; this image carries
+  scikit-learn 1.9.0 / scipy 1.18.1 / numpy 2.3.5, recorded in every golden
+  file).
+* ``OracleGP``: a restatement of ``gpkernels.GP_RBFW`` (``gpkernels.py:299-649``)
+  that, like the reference, drives scikit-learn's ``GaussianProcessRegressor``
+  (alpha=0, kernel ``C*RBF + White``) and SciPy's L-BFGS-B.  It is what
+  ``bench.py`` times as the CPU baseline (kind "port").
+
+Parity pinning: the reference ships no tests or golden vectors,
+so the oracle is pinned against outputs of the *unmodified* reference
+``GP_RBFW`` executed in the build container (``oracle/ref_import.py`` +
+``oracle/make_golden.py`` -> ``tests/golden/*.npz``); ``tests/test_oracle.py``
+checks both restatements against those fixtures.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import scipy.linalg as la
+
+LOG_2PI = float(np.log(2.0 * np.pi))
+
+
+# --------------------------------------------------------------------------
+# Plain NumPy restatement of the arithmetic
+# --------------------------------------------------------------------------
+def np_kernel(t, theta, t2=None, eval_gradient=False):
+    """K(theta) = sigma^2 * R + chi * I and (optionally) dK/dtheta.
+
+    Follows sklearn ``kernels.py``: RBF ``:1559-1578`` (X/ell, squared
+    euclidean distance, exp(-d/2), diagonal forced to 1), ConstantKernel
+    ``:1279-1292``, Product ``:966-969``, WhiteKernel ``:1407-1419`` (zero when
+    a second argument is given), Sum ``:866-869``.  ``theta`` is the log-space
+    vector (log sigma^2, log ell, log chi) -- ``kernels.py:290-362``.
+    """
+    sig2, ell, chi = np.exp(np.asarray(theta, dtype=np.float64))
+    x = np.asarray(t, dtype=np.float64) / ell
+    if t2 is None:
+        d = (x[:, None] - x[None, :]) ** 2
+        R = np.exp(-0.5 * d)
+        np.fill_diagonal(R, 1.0)
+        K = sig2 * R
+        K[np.diag_indices_from(K)] += chi
+        if not eval_gradient:
+            return K
+        dK = np.empty(K.shape + (3,))
+        dK[..., 0] = sig2 * R
+        dK[..., 1] = sig2 * (R * d)
+        dK[..., 2] = chi * np.eye(K.shape[0])
+        return K, dK
+    x2 = np.asarray(t2, dtype=np.float64) / ell
+    d = (x[:, None] - x2[None, :]) ** 2
+    return sig2 * np.exp(-0.5 * d)
+
+
+def np_lml_grad(t, y, theta):
+    """Log marginal likelihood and its gradient w.r.t. log-hyperparameters.
+
+    Follows ``GaussianProcessRegressor.log_marginal_likelihood`` (sklearn
+    ``_gpr.py:583-651``): Cholesky (failure -> (-inf, 0), ``:589-593``),
+    alpha = K^-1 y, LML = -1/2 y'alpha - sum log L_ii - m/2 log 2pi
+    (``:613-617``), gradient 1/2 tr((alpha alpha' - K^-1) dK/dtheta_j)
+    (``:629-651``).  Returns (lml, grad[3], status) with status 0 ok / 1 not PD.
+    """
+    y = np.asarray(y, dtype=np.float64)
+    K, dK = np_kernel(t, theta, eval_gradient=True)
+    try:
+        L = la.cholesky(K, lower=True, check_finite=False)
+    except la.LinAlgError:
+        return -np.inf, np.zeros(3), 1
+    alpha = la.cho_solve((L, True), y, check_finite=False)
+    lml = -0.5 * float(y @ alpha) - float(np.log(np.diag(L)).sum())
+    lml -= 0.5 * K.shape[0] * LOG_2PI
+    Kinv = la.cho_solve((L, True), np.eye(K.shape[0]), check_finite=False)
+    inner = np.outer(alpha, alpha) - Kinv
+    grad = 0.5 * np.einsum("ij,jik->k", inner, dK)
+    return lml, grad, 0
+
+
+def np_alpha(t, y, theta):
+    """alpha_ = K^-1 y at fixed theta (sklearn ``_gpr.py:349-367``)."""
+    K = np_kernel(t, theta)
+    L = la.cholesky(K, lower=True, check_finite=False)
+    return la.cho_solve((L, True), np.asarray(y, dtype=np.float64), check_finite=False), L
+
+
+def np_predict(t, y, theta, t_star):
+    """Posterior mean and standard deviation (sklearn ``_gpr.py:444-500``).
+
+    mean = sigma^2 R(t*, t) alpha (no white-noise term in the cross kernel);
+    var = (sigma^2 + chi) - sum_k V_ki^2, V = L^-1 k*', clipped at 0.
+    """
+    alpha, L = np_alpha(t, y, theta)
+    Ks = np_kernel(t_star, theta, t2=t)
+    mean = Ks @ alpha
+    V = la.solve_triangular(L, Ks.T, lower=True, check_finite=False)
+    sig2, _, chi = np.exp(np.asarray(theta, dtype=np.float64))
+    var = (sig2 + chi) - np.einsum("ij,ij->j", V, V)
+    var[var < 0] = 0.0
+    return mean, np.sqrt(var)
+
+
+def np_rbf_eval(t1, t2, sig2, ell):
+    """kappa(t1, t2) = sigma^2 exp(-(t1 - t2)^2 / (2 ell^2)) (``gpkernels.py:591-609``)."""
+    tdiff = np.asarray(t1)[:, None] - np.asarray(t2)
+    return sig2 * np.exp(-(tdiff**2) / (2 * ell**2))
+
+
+def np_lstsq_moments(t, y, theta, t_est, eta=1e-8, want_sqrtW=True):
+    """state/derivative estimates, derivative covariance and sqrtW.
+
+    Follows ``GP_RBFW.compute_lstsq_matrices`` (``gpkernels.py:612-649``) and
+    ``_BaseGP._compute_estimates_and_weights`` (``gpkernels.py:445-504``).
+    """
+    sig2, ell, chi = np.exp(np.asarray(theta, dtype=np.float64))
+    t = np.asarray(t, dtype=np.float64)
+    t_est = np.asarray(t_est, dtype=np.float64)
+    rbf_yy = np_rbf_eval(t, t, sig2, ell)
+    rbf_zy = np_rbf_eval(t_est, t, sig2, ell)
+    rbf_zz = np_rbf_eval(t_est, t_est, sig2, ell)
+    dzz = t_est[:, None] - t_est
+    dzy = t_est[:, None] - t
+    ell2 = ell**2
+    K_yy = rbf_yy + np.diag(np.full(t.size, chi))
+    K_zy = -dzy * rbf_zy / ell2
+    K_zz = (1 - (dzz**2 / ell2)) * rbf_zz / ell2
+
+    cf = la.cho_factor(K_yy, check_finite=True)
+    a = la.cho_solve(cf, np.asarray(y, dtype=np.float64))
+    state = rbf_zy @ a
+    ddt = K_zy @ a
+    X = K_zy @ la.cho_solve(cf, K_zy.T)
+    X = 0.5 * (X + X.T)
+    C = K_zz - X
+    out = dict(state_estimate=state, ddt_estimate=ddt, ddt_covariance=C)
+    if want_sqrtW:
+        out["sqrtW"] = np_sqrtW(C, eta)
+    return out
+
+
+def np_sqrtW(C, eta):
+    """sqrtW = (C + eta I)^(-1/2) via eigh (``gpkernels.py:496-504``)."""
+    ev, V = la.eigh(C + eta * np.eye(C.shape[0]), check_finite=False)
+    if np.any(ev <= 0):
+        raise ValueError("inverse covariance not positive definite, increase eta")
+    return V @ np.diag(1 / np.sqrt(ev)) @ V.T
+
+
+# --------------------------------------------------------------------------
+# Restatement of gpkernels.GP_RBFW on top of scikit-learn (as the reference)
+# --------------------------------------------------------------------------
+class OracleGP:
+    """Port of ``gpkernels.GP_RBFW`` (``gpkernels.py:507-649``) + ``_BaseGP``
+    (``:299-504``): sklearn ``GaussianProcessRegressor(kernel=C*RBF+White,
+    alpha=0, n_restarts_optimizer=...)``; restart points come from the global
+    NumPy RNG exactly as in the reference (``_gpr.py:251,330``)."""
+
+    def __init__(self, constant_bounds, length_scale_bounds, noise_level_bounds,
+                 n_restarts_optimizer):
+        from sklearn.gaussian_process import GaussianProcessRegressor
+        from sklearn.gaussian_process.kernels import RBF, ConstantKernel, WhiteKernel
+
+        kernel = (
+            ConstantKernel(1.0, constant_value_bounds=constant_bounds)
+            * RBF(length_scale_bounds=length_scale_bounds)
+        ) + WhiteKernel(noise_level_bounds=noise_level_bounds)
+        self.gpr = GaussianProcessRegressor(
+            kernel=kernel, n_restarts_optimizer=n_restarts_optimizer, alpha=0
+        )
+
+    # gpkernels.py:330-348
+    def fit(self, t_training, training_data):
+        if training_data.ndim > 1:
+            raise ValueError("GP training data must be one-dimensional")
+        self.t_training = t_training
+        self.y = training_data
+        self.gpr.fit(t_training[:, None], training_data)
+        return self
+
+    # gpkernels.py:350-365
+    def predict(self, t):
+        return self.gpr.predict(t[:, None], return_std=True)
+
+    @property
+    def theta(self):
+        return np.array(self.gpr.kernel_.theta)
+
+    @property
+    def lml(self):
+        return float(self.gpr.log_marginal_likelihood_value_)
+
+    def lml_grad(self, theta):
+        return self.gpr.log_marginal_likelihood(np.asarray(theta), eval_gradient=True)
+
+    # gpkernels.py:612-649 / 445-504
+    def compute_lstsq_matrices(self, t_est, eta=1e-8, want_sqrtW=True):
+        out = np_lstsq_moments(self.t_training, self.y, self.theta, t_est, eta, want_sqrtW)
+        self.t_estimation = t_est
+        for k, v in out.items():
+            setattr(self, k, v)
+        return self
+
+
+def oracle_fit_gaussian_processes(t_est, t_sampled, snapshots, bounds, n_restarts,
+                                  eta=1e-8, want_sqrtW=True):
+    """Port of ``fit_gaussian_processes`` (``PDEs/step2_fitgps.py:67-102``; a list of
+    per-variable time vectors gives the ODE flavour, ``ODEs/step2_fitgps.py:68-97``)."""
+    gps = []
+    for i in range(snapshots.shape[0]):
+        ti = t_sampled[i] if isinstance(t_sampled, (list, tuple)) else t_sampled
+        gp = OracleGP(bounds[0], bounds[1], bounds[2], n_restarts)
+        gp.fit(np.asarray(ti), np.asarray(snapshots[i]))
+        gp.compute_lstsq_matrices(t_est, eta=eta, want_sqrtW=want_sqrtW)
+        gps.append(gp)
+    return gps
+
+
+# --------------------------------------------------------------------------
+# Synthetic workload of BASELINE.json's configs[3]/[4]
+# --------------------------------------------------------------------------
+def synthetic_trajectories(r, m, seed=0):
+    """t = sort(U(0,1)) with endpoints forced, y_i = sum_k a sin(2 pi f t + phi) + 0.03 N(0,1)."""
+    rng = np.random.default_rng(seed)
+    t = np.sort(rng.uniform(0.0, 1.0, size=m))
+    t[0], t[-1] = 0.0, 1.0
+    a = rng.uniform(0.5, 2.0, size=(r, 3))
+    f = rng.uniform(1.0, 8.0, size=(r, 3))
+    ph = rng.uniform(0.0, 2 * np.pi, size=(r, 3))
+    y = (a[:, :, None] * np.sin(2 * np.pi * f[:, :, None] * t[None, None, :] + ph[:, :, None])).sum(1)
+    y += 0.03 * rng.standard_normal((r, m))
+    return t, y
