@@ -133,12 +133,16 @@ __device__ __forceinline__ bool potf2_trtri_smem(double* P, double* dval, double
         const int c = tid >> 1, h = tid & 1;
         double* xrow = P + c * LDP;
         const double xc = dinv[c];
-        for (int i = c + 1; i < TB; ++i) {
+        // warp-uniform trip count (columns of one warp are 16 consecutive c): lanes with i <= c idle
+        for (int i = (tid >> 5) * 16 + 1; i < TB; ++i) {
             const double* Li = P + i * LDP;
-            double s = (h == 0) ? Li[c] * xc : 0.0;
-            for (int k = c + 1 + h; k < i; k += 2) s += Li[k] * xrow[k];
+            double s = 0.0;
+            if (i > c) {
+                if (h == 0) s = Li[c] * xc;
+                for (int k = c + 1 + h; k < i; k += 2) s += Li[k] * xrow[k];
+            }
             s += __shfl_xor_sync(0xffffffffu, s, 1);
-            if (h == 0) xrow[i] = -s * dinv[i];
+            if (h == 0 && i > c) xrow[i] = -s * dinv[i];
             __syncwarp();
         }
     }

@@ -1,0 +1,105 @@
+"""world_size-2 gloo test of the (GP x start) sharding + all-gather logic, with a CPU stand-in engine."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+
+class FakeEngine:
+    """Deterministic stand-in for _lib.Context: results are pure functions of the inputs, so the sharded
+    run must reproduce the single-process run exactly."""
+
+    def fit(self, T, Y, bounds_log, starts, gp_of=None, opts=None):
+        B = starts.shape[0]
+        theta = np.clip(starts * 0.5 + Y[gp_of, :3] * 0.01, bounds_log[:, 0], bounds_log[:, 1])
+        fun = (theta ** 2).sum(1) + T[gp_of].sum(1)
+        return dict(theta=theta, fun=fun, nfev=np.full(B, 7, np.int32), nit=np.full(B, 3, np.int32),
+                    status=(np.asarray(gp_of) % 2).astype(np.int32), evals=7 * B, rounds=7)
+
+    def lstsq_moments(self, T, Y, theta, t_est, want_cov=True):
+        G = T.shape[0]
+        state = theta[:, :1] * t_est[None, :]
+        ddt = Y.sum(1)[:, None] + t_est[None, :]
+        cov = np.einsum("g,i,j->gij", theta[:, 1], t_est, t_est) if want_cov else None
+        return state, ddt, cov, np.zeros(G, np.int32)
+
+    def predict(self, T, Y, theta, t_star, want_alpha=False):
+        G = T.shape[0]
+        alpha = Y * theta[:, 2:3]
+        return np.zeros((G, 1)), np.zeros((G, 1)), alpha, np.zeros(G, np.int32)
+
+
+def _problem():
+    rng = np.random.default_rng(5)
+    G, m, S = 5, 12, 7
+    T = np.sort(rng.uniform(0, 1, (G, m)), axis=1)
+    Y = rng.standard_normal((G, m))
+    bl = np.array([[-3.0, 3.0], [-2.0, 2.0], [-5.0, 1.0]])
+    starts = rng.uniform(bl[:, 0], bl[:, 1], size=(G * S, 3))
+    gp_of = np.repeat(np.arange(G, dtype=np.int32), S)
+    return T, Y, bl, starts, gp_of
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    from gpbo_pkg import pkg
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    T, Y, bl, starts, gp_of = _problem()
+    eng = FakeEngine()
+    res = pkg.sharding.fit_pairs(eng, T, Y, bl, starts, gp_of, group=True)
+    G = T.shape[0]
+    funs = res["fun"].reshape(G, -1)
+    theta_opt = res["theta"].reshape(G, -1, 3)[np.arange(G), funs.argmin(1)]
+    mom = pkg.sharding.moments(eng, T, Y, theta_opt, np.linspace(0, 1, 6), group=True)
+    owned = [g for g in range(G) if mom["cov"][g] is not None]
+    q.put((rank, res["theta"], res["fun"], res["status"], mom["alpha"], mom["state"], mom["ddt"], owned))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_fit_and_moments_match_single_process():
+    from gpbo_pkg import pkg
+
+    T, Y, bl, starts, gp_of = _problem()
+    eng = FakeEngine()
+    ref = pkg.sharding.fit_pairs(eng, T, Y, bl, starts, gp_of, group=None)
+    G = T.shape[0]
+    theta_opt = ref["theta"].reshape(G, -1, 3)[np.arange(G), ref["fun"].reshape(G, -1).argmin(1)]
+    refm = pkg.sharding.moments(eng, T, Y, theta_opt, np.linspace(0, 1, 6), group=None)
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    owned_all = []
+    for rank, theta, fun, status, alpha, state, ddt, owned in outs:
+        assert np.array_equal(theta, ref["theta"]) and np.array_equal(fun, ref["fun"])
+        assert np.array_equal(status, ref["status"])
+        assert np.array_equal(alpha, refm["alpha"]) and np.array_equal(state, refm["state"])
+        assert np.array_equal(ddt, refm["ddt"])
+        assert owned == list(range(rank, G, 2))      # covariance stays on the owning rank
+        owned_all += owned
+    assert sorted(owned_all) == list(range(G))
+
+
+def test_shard_indices_cover_everything_once():
+    from gpbo_pkg import pkg
+
+    for n in (0, 1, 7, 64, 2112):
+        for w in (1, 2, 4, 8):
+            allidx = np.concatenate([pkg.sharding.shard_indices(n, r, w) for r in range(w)])
+            assert sorted(allidx.tolist()) == list(range(n))
