@@ -160,6 +160,9 @@ int set_kernel_attrs() {
     CUDA_TRY(cudaFuncSetAttribute(trtri_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(lauum_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
+#define GPBO_SYM_ATTR(K) CUDA_TRY(cudaFuncSetAttribute(assemble_sym_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, SYM_SMEM));
+    GPBO_SYM_ATTR(0) GPBO_SYM_ATTR(1) GPBO_SYM_ATTR(2) GPBO_SYM_ATTR(3) GPBO_SYM_ATTR(4) GPBO_SYM_ATTR(5) GPBO_SYM_ATTR(6)
+#undef GPBO_SYM_ATTR
     g_attr_done = true;
     return GPBO_OK;
 }
@@ -327,10 +330,23 @@ int gpbo_assemble(gpbo_ctx* c, int kind, const double* t1, long t1_stride, int n
     if (!c || !t1 || !t2 || !theta || !out || n1 <= 0 || n2 <= 0 || B <= 0 || kind < 0 || kind > 6)
         return fail(GPBO_EINVAL, "assemble: bad argument");
     CUDA_TRY(cudaSetDevice(c->device));
+    if (int rc = set_kernel_attrs()) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    dim3 grid((n2 + 2 * NTHR - 1) / (2 * NTHR), (n1 + ASM_ROWS - 1) / ASM_ROWS, B);
+    const long os = (long)n1 * n2;
+    const bool sym = (t1 == t2 && t1_stride == t2_stride && n1 == n2);
     launch(c, C_ASM, s, [&] {
-        assemble_kernel<<<grid, NTHR, 0, s>>>(kind, t1, t1_stride, n1, t2, t2_stride, n2, theta, B, out, (long)n1 * n2);
+        if (sym) {
+            const int nt = (n1 + SYM_T - 1) / SYM_T;
+            dim3 grid(nt * (nt + 1) / 2, B);
+#define GPBO_ASM_SYM(K) case K: assemble_sym_kernel<K><<<grid, NTHR, SYM_SMEM, s>>>(t1, t1_stride, n1, theta, out, os); break;
+            switch (kind) { GPBO_ASM_SYM(0) GPBO_ASM_SYM(1) GPBO_ASM_SYM(2) GPBO_ASM_SYM(3) GPBO_ASM_SYM(4) GPBO_ASM_SYM(5) GPBO_ASM_SYM(6) }
+#undef GPBO_ASM_SYM
+        } else {
+            dim3 grid((n2 + ASM_COLS - 1) / ASM_COLS, (n1 + ASM_ROWS - 1) / ASM_ROWS, B);
+#define GPBO_ASM_GEN(K) case K: assemble_general_kernel<K><<<grid, NTHR, 0, s>>>(t1, t1_stride, n1, t2, t2_stride, n2, theta, out, os); break;
+            switch (kind) { GPBO_ASM_GEN(0) GPBO_ASM_GEN(1) GPBO_ASM_GEN(2) GPBO_ASM_GEN(3) GPBO_ASM_GEN(4) GPBO_ASM_GEN(5) GPBO_ASM_GEN(6) }
+#undef GPBO_ASM_GEN
+        }
     });
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(s));

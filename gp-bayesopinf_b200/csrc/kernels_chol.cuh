@@ -40,18 +40,18 @@ struct AsmSklearn {
         if (r >= m || c >= m) return r == c ? 1.0 : 0.0;
         if (r == c) return sig2 + chi;
         const double d = xr - xc;
-        return sig2 * exp(-0.5 * (d * d));
+        return sig2 * gpbo_exp(-0.5 * (d * d));
     }
 };
 // rbf_eval order (gpkernels.py:608-609, 639): kappa = sigma^2 exp(-(ti-tj)^2 / (2 ell^2)), + chi on the diagonal.
 struct AsmRbfEval {
-    double sig2, chi, two_ell2;
+    double sig2, chi, two_ell2, r_two_ell2;
     int m;
     __device__ __forceinline__ double operator()(int r, int c, double tr, double tcn) const {
         if (r >= m || c >= m) return r == c ? 1.0 : 0.0;
         if (r == c) return sig2 + chi;
         const double d = tr - tcn;
-        return sig2 * exp(-(d * d) / two_ell2);
+        return sig2 * gpbo_exp(-gpbo_div(d * d, two_ell2, r_two_ell2));
     }
 };
 
@@ -66,7 +66,7 @@ template <>
 struct AsmSelect<1> {
     using type = AsmRbfEval;
     static __device__ __forceinline__ type make(const PairParams& q, int m) {
-        return {q.sig2, q.chi, 2 * (q.ell * q.ell), m};
+        return {q.sig2, q.chi, 2 * (q.ell * q.ell), 0.5 * q.inv_ell2, m};
     }
 };
 
@@ -159,10 +159,14 @@ __global__ void __launch_bounds__(NTHR, 1) chol_diag_kernel(MatArgs a, int j) {
     const int p = blockIdx.x;
     double* Ap = a.A + (long)p * a.mat_stride;
     const double* rows = Ap + (long)j * TB * a.lda;
+    __shared__ uint64_t bars[2 * NSTAGE];
+    Ring ring;
+    ring_init(ring, bars);
     Acc acc;
     acc_zero(acc);
-    auto fa = [&](int kt) { return rows + kt * BK; };
-    gemm_nt_loop<true>(acc, fa, a.lda, fa, a.lda, j * (TB / BK), smem, tc);
+    gemm_nt_loop<true>(acc, [&](int kt) { return SliceSrc{rows + kt * BK, a.lda, nullptr, 0}; }, j * (TB / BK), smem,
+                       ring, tc);
+    __syncthreads();   // every warp is done with the ring: its memory becomes P
 
     double* P = smem;
     double* dval = smem + TB * LDP;
@@ -219,10 +223,11 @@ __device__ __forceinline__ double cross_element(int kind, const PairParams& q, i
                                                 double xr, double xc) {
     if (r >= nrow || c >= m) return 0.0;
     const double d = xr - xc;
-    if (kind == 0) return q.sig2 * exp(-0.5 * (d * d));
-    const double kap = q.sig2 * exp(-(d * d) / (2 * (q.ell * q.ell)));
+    if (kind == 0) return q.sig2 * gpbo_exp(-0.5 * (d * d));
+    const double ell2 = q.ell * q.ell;
+    const double kap = q.sig2 * gpbo_exp(-gpbo_div(d * d, 2 * ell2, 0.5 * q.inv_ell2));
     if (kind == 1) return kap;
-    return -d * kap / (q.ell * q.ell);     // gpkernels.py:640
+    return gpbo_div(-d * kap, ell2, q.inv_ell2);     // gpkernels.py:640
 }
 
 // ---- Cholesky panel / triangular solve with many right-hand sides -------------------------
@@ -243,13 +248,16 @@ chol_panel_kernel(MatArgs a, int j, double* X, long x_stride, int xT, CrossArgs 
     double* Xp = CROSS ? X + (long)p * x_stride : a.A + (long)p * a.mat_stride;
     const double* arows = Xp + (long)i * TB * a.lda;
     const double* brows = Ap + (long)j * TB * a.lda;
+    __shared__ uint64_t bars[2 * NSTAGE];
+    Ring ring;
+    ring_init(ring, bars);
     Acc acc;
     acc_zero(acc);
-    gemm_nt_loop<false>(acc, [&](int kt) { return arows + kt * BK; }, a.lda,
-                        [&](int kt) { return brows + kt * BK; }, a.lda, j * (TB / BK), smem, tc);
+    gemm_nt_loop<false>(acc, [&](int kt) { return SliceSrc{arows + kt * BK, a.lda, brows + kt * BK, a.lda}; },
+                        j * (TB / BK), smem, ring, tc);
 
     double* S = smem;
-    double* ring = smem + TB * LDS;
+    double* stages = smem + TB * LDS;
     {
         const PairParams q = a.pp[p];
         double xr[8], xc[4][2];
@@ -272,11 +280,13 @@ chol_panel_kernel(MatArgs a, int j, double* X, long x_stride, int xT, CrossArgs 
                     acc.v[mi][ni][e] = kv - acc.v[mi][ni][e];
                 }
     }
+    __syncthreads();   // ring memory is re-used for S
     acc_to_smem<LDS>(acc, S, tc);
+    __syncthreads();
     Acc out;
     acc_zero(out);
     const double* Dj = a.D + ((long)p * a.T + j) * (TB * TB);
-    epi_product_SxDt(out, S, Dj, ring, tc);
+    epi_product_SxDt(out, S, Dj, stages, ring, tc);
     double* dst = Xp + (long)i * TB * a.lda + j * TB;
 #pragma unroll
     for (int mi = 0; mi < 8; ++mi)
@@ -384,21 +394,28 @@ __global__ void __launch_bounds__(NTHR, 1) trtri_row_kernel(MatArgs a, int i) {
     const double* Lrow = Ap + (long)i * TB * a.lda;          // L[i-block rows][*]
     const double* Urow = Ap + (long)j * TB * a.lda;          // U[j-block rows][*]
     const double* DTj = a.DT + ((long)p * a.T + j) * (TB * TB);
+    __shared__ uint64_t bars[2 * NSTAGE];
+    Ring ring;
+    ring_init(ring, bars);
     Acc acc;
     acc_zero(acc);
-    // k-block j: B[n][k] = W_jj[k][n] = DT_j[n][k]
-    gemm_nt_loop<false>(acc, [&](int kt) { return Lrow + j * TB + kt * BK; }, a.lda,
-                        [&](int kt) { return DTj + kt * BK; }, TB, TB / BK, smem, tc);
-    // k-blocks j+1 .. i-1: B[n][k] = U[j*128+n][k]
-    gemm_nt_loop<false>(acc, [&](int kt) { return Lrow + (j + 1) * TB + kt * BK; }, a.lda,
-                        [&](int kt) { return Urow + (j + 1) * TB + kt * BK; }, a.lda, (i - j - 1) * (TB / BK), smem, tc);
+    // k-block j: B[n][k] = W_jj[k][n] = DT_j[n][k];  k-blocks j+1 .. i-1: B[n][k] = U[j*128+n][k]
+    gemm_nt_loop<false>(
+        acc,
+        [&](int kt) {
+            const double* ap = Lrow + j * TB + kt * BK;
+            return kt < TB / BK ? SliceSrc{ap, a.lda, DTj + kt * BK, TB} : SliceSrc{ap, a.lda, Urow + j * TB + kt * BK, a.lda};
+        },
+        (i - j) * (TB / BK), smem, ring, tc);
     double* G = smem;
-    double* ring = smem + TB * LDS;
+    double* stages = smem + TB * LDS;
+    __syncthreads();   // ring memory is re-used for G
     acc_to_smem<LDS>(acc, G, tc);      // G[k][n]
+    __syncthreads();
     Acc out;
     acc_zero(out);
     const double* Di = a.D + ((long)p * a.T + i) * (TB * TB);
-    epi_product_DxG(out, Di, G, ring, tc);
+    epi_product_DxG(out, Di, G, stages, ring, tc);
     // transposed store: U[j*128 + col][i*128 + row] = -out[row][col]
     double* dst = Ap + (long)j * TB * a.lda + i * TB;
 #pragma unroll
@@ -429,20 +446,31 @@ lauum_grad_kernel(MatArgs a, const double* __restrict__ alpha, double* __restric
     const double* UI = Ap + (long)I * TB * a.lda;
     const double* UJ = Ap + (long)J * TB * a.lda;
     const double* DTI = a.DT + ((long)p * a.T + I) * (TB * TB);
+    __shared__ uint64_t bars[2 * NSTAGE];
+    Ring ring;
+    ring_init(ring, bars);
     Acc acc;
     acc_zero(acc);
+    // k-block I comes from the diagonal-block inverse DT_I (row stride 128), k-blocks I+1.. from U (row stride lda)
+    const int nk = (a.T - I) * (TB / BK);
     if (I == J) {
-        gemm_nt_loop<true>(acc, [&](int kt) { return DTI + kt * BK; }, TB, [&](int kt) { return DTI + kt * BK; }, TB,
-                           TB / BK, smem, tc);
-        auto f = [&](int kt) { return UI + (I + 1) * TB + kt * BK; };
-        gemm_nt_loop<true>(acc, f, a.lda, f, a.lda, (a.T - 1 - I) * (TB / BK), smem, tc);
+        gemm_nt_loop<true>(
+            acc,
+            [&](int kt) {
+                return kt < TB / BK ? SliceSrc{DTI + kt * BK, TB, nullptr, 0}
+                                    : SliceSrc{UI + I * TB + kt * BK, a.lda, nullptr, 0};
+            },
+            nk, smem, ring, tc);
     } else {
-        gemm_nt_loop<false>(acc, [&](int kt) { return DTI + kt * BK; }, TB,
-                            [&](int kt) { return UJ + I * TB + kt * BK; }, a.lda, TB / BK, smem, tc);
-        gemm_nt_loop<false>(acc, [&](int kt) { return UI + (I + 1) * TB + kt * BK; }, a.lda,
-                            [&](int kt) { return UJ + (I + 1) * TB + kt * BK; }, a.lda, (a.T - 1 - I) * (TB / BK),
-                            smem, tc);
+        gemm_nt_loop<false>(
+            acc,
+            [&](int kt) {
+                const double* bp = UJ + I * TB + kt * BK;
+                return kt < TB / BK ? SliceSrc{DTI + kt * BK, TB, bp, a.lda} : SliceSrc{UI + I * TB + kt * BK, a.lda, bp, a.lda};
+            },
+            nk, smem, ring, tc);
     }
+    __syncthreads();   // ring memory is re-used by block_sum
     const PairParams pr = a.pp[p];
     const double* tsp = a.ts + (long)p * a.lda;
     const double* al = alpha + (long)p * a.lda;
@@ -469,7 +497,7 @@ lauum_grad_kernel(MatArgs a, const double* __restrict__ alpha, double* __restric
                     } else {
                         const double d = xr[mi] - xc[ni][e];
                         const double d2 = d * d;
-                        const double kr = pr.sig2 * exp(-0.5 * d2);
+                        const double kr = pr.sig2 * gpbo_exp(-0.5 * d2);
                         s[0] += w * kr;
                         s[1] += w * (kr * d2);
                     }

@@ -63,14 +63,17 @@ schur_kernel(MatArgs a, const double* __restrict__ X, long x_stride, CrossArgs c
     const int J = q - I * (I + 1) / 2;
     const double* XI = X + (long)p * x_stride + (long)I * TB * a.lda;
     const double* XJ = X + (long)p * x_stride + (long)J * TB * a.lda;
+    __shared__ uint64_t bars[2 * NSTAGE];
+    Ring ring;
+    ring_init(ring, bars);
     Acc acc;
     acc_zero(acc);
     if (I == J) {
-        auto f = [&](int kt) { return XI + kt * BK; };
-        gemm_nt_loop<true>(acc, f, a.lda, f, a.lda, a.lda / BK, smem, tc);
+        gemm_nt_loop<true>(acc, [&](int kt) { return SliceSrc{XI + kt * BK, a.lda, nullptr, 0}; }, a.lda / BK, smem,
+                           ring, tc);
     } else {
-        gemm_nt_loop<false>(acc, [&](int kt) { return XI + kt * BK; }, a.lda, [&](int kt) { return XJ + kt * BK; },
-                            a.lda, a.lda / BK, smem, tc);
+        gemm_nt_loop<false>(acc, [&](int kt) { return SliceSrc{XI + kt * BK, a.lda, XJ + kt * BK, a.lda}; },
+                            a.lda / BK, smem, ring, tc);
     }
     const PairParams pr = a.pp[p];
     const double ell2 = pr.ell * pr.ell;
@@ -94,8 +97,8 @@ schur_kernel(MatArgs a, const double* __restrict__ X, long x_stride, CrossArgs c
                 if (r < n && c < n && c <= r) {
                     const double d = xr[mi] - xc[ni][e];
                     const double d2 = d * d;
-                    const double kap = pr.sig2 * exp(-d2 / (2 * ell2));
-                    const double kzz = (1 - (d2 / ell2)) * kap / ell2;
+                    const double kap = pr.sig2 * gpbo_exp(-gpbo_div(d2, 2 * ell2, 0.5 * pr.inv_ell2));
+                    const double kzz = gpbo_div((1 - gpbo_div(d2, ell2, pr.inv_ell2)) * kap, ell2, pr.inv_ell2);
                     const double v = kzz - acc.v[mi][ni][e];
                     Cp[(long)r * n + c] = v;
                     if (r != c) Cp[(long)c * n + r] = v;
@@ -121,56 +124,146 @@ __global__ void scale_rows_kernel(const double* __restrict__ src, long src_strid
 //       4 K_zy = -(t1-t2) kappa / ell^2                            gpkernels.py:640
 //       5 K_zz = (1 - (t1-t2)^2/ell^2) kappa / ell^2               gpkernels.py:641
 //       6 dK/dlog(ell) = sigma^2 R (x1-x2)^2                       kernels.py:1575-1577, 966-969
-// Each thread produces two adjacent columns (one 16-byte store); a warp covers 512 contiguous
-// bytes of a row; a CTA covers ASM_ROWS rows x 512 columns.
-constexpr int ASM_ROWS = 8;
+// The element generators keep each reference expression's operation order (x = t/ell is a true
+// division done once per abscissa; divisions by ell^2 / 2 ell^2 use gpbo_div); exp is gpbo_exp.
+// An element costs ~20 FP64-pipe instructions, which at 64 FP64 op/clk/SM is within ~10 % of what the
+// HBM write stream needs, so
+//  * the general kernel (t1 != t2) writes each row segment with 16-byte stores, 512 contiguous bytes
+//    per warp, one 32 x 512 tile per CTA;
+//  * when t1 == t2 (train matrices, K_zz, dK/dlog ell) the symmetric kernel evaluates only tiles
+//    I >= J (64 x 64), stages the tile and its transpose in shared memory and streams both out as
+//    fully coalesced 512-byte rows: half the FP64 work, so the kernel is HBM-write bound.
+struct AsmConsts {
+    double sig2, ell, chi, ell2, two_ell2, r_ell2, r_two_ell2;
+    __device__ __forceinline__ AsmConsts(const double* theta) {
+        sig2 = exp(theta[0]); ell = exp(theta[1]); chi = exp(theta[2]);
+        ell2 = ell * ell; two_ell2 = 2 * ell2; r_ell2 = 1.0 / ell2; r_two_ell2 = 0.5 * r_ell2;
+    }
+};
 
-__device__ __forceinline__ double assemble_element(int kind, double sig2, double ell, double chi, double ell2, int r,
-                                                   int c, double x1, double x2) {
+template <int KIND>
+__device__ __forceinline__ double assemble_element(const AsmConsts& k, bool diag, double x1, double x2) {
     const double d = x1 - x2;
     const double d2 = d * d;
-    switch (kind) {
-        case 0: return r == c ? sig2 + chi : sig2 * exp(-0.5 * d2);
-        case 1: return r == c ? sig2 + chi : sig2 * exp(-d2 / (2 * ell2));
-        case 2: return sig2 * exp(-0.5 * d2);
-        case 3: return sig2 * exp(-d2 / (2 * ell2));
-        case 4: return -d * (sig2 * exp(-d2 / (2 * ell2))) / ell2;
-        case 5: return (1 - (d2 / ell2)) * (sig2 * exp(-d2 / (2 * ell2))) / ell2;
-        default: return sig2 * (exp(-0.5 * d2) * d2);
-    }
+    if (KIND == 0) return diag ? k.sig2 + k.chi : k.sig2 * gpbo_exp(-0.5 * d2);
+    if (KIND == 1) return diag ? k.sig2 + k.chi : k.sig2 * gpbo_exp(-gpbo_div(d2, k.two_ell2, k.r_two_ell2));
+    if (KIND == 2) return k.sig2 * gpbo_exp(-0.5 * d2);
+    if (KIND == 6) return k.sig2 * (gpbo_exp(-0.5 * d2) * d2);
+    const double kap = k.sig2 * gpbo_exp(-gpbo_div(d2, k.two_ell2, k.r_two_ell2));
+    if (KIND == 3) return kap;
+    if (KIND == 4) return gpbo_div(-d * kap, k.ell2, k.r_ell2);
+    return gpbo_div((1 - gpbo_div(d2, k.ell2, k.r_ell2)) * kap, k.ell2, k.r_ell2);
 }
 
+template <int KIND>
+struct AsmScaled { static constexpr bool value = (KIND == 0 || KIND == 2 || KIND == 6); };
+
+constexpr int ASM_ROWS = 32;     // rows per CTA of the general kernel
+constexpr int ASM_COLS = 2 * NTHR;
+
+template <int KIND>
 __global__ void __launch_bounds__(NTHR)
-assemble_kernel(int kind, const double* __restrict__ t1, long t1_stride, int n1, const double* __restrict__ t2,
-                long t2_stride, int n2, const double* __restrict__ theta, int B, double* __restrict__ out,
-                long out_stride) {
+assemble_general_kernel(const double* __restrict__ t1, long t1_stride, int n1, const double* __restrict__ t2,
+                        long t2_stride, int n2, const double* __restrict__ theta, double* __restrict__ out,
+                        long out_stride) {
+    __shared__ double x1s[ASM_ROWS];
     const int p = blockIdx.z;
-    const double sig2 = exp(theta[3 * p]), ell = exp(theta[3 * p + 1]), chi = exp(theta[3 * p + 2]);
-    const double ell2 = ell * ell;
-    const bool scaled = (kind == 0 || kind == 2 || kind == 6);
-    const int c0 = blockIdx.x * (2 * NTHR) + 2 * threadIdx.x;
+    const AsmConsts k(theta + 3 * p);
+    constexpr bool scaled = AsmScaled<KIND>::value;
+    const int c0 = blockIdx.x * ASM_COLS + 2 * threadIdx.x;
     const int r0 = blockIdx.y * ASM_ROWS;
-    if (c0 >= n2) return;
     const double* a1 = t1 + (long)p * t1_stride;
     const double* a2 = t2 + (long)p * t2_stride;
+    if (threadIdx.x < ASM_ROWS) {
+        const int r = r0 + threadIdx.x;
+        double v = r < n1 ? a1[r] : 0.0;
+        if (scaled) v = v / k.ell;
+        x1s[threadIdx.x] = v;
+    }
+    __syncthreads();
+    if (c0 >= n2) return;
     const bool two = (c0 + 1 < n2);
     double x2a = a2[c0], x2b = two ? a2[c0 + 1] : 0.0;
-    if (scaled) { x2a = x2a / ell; x2b = x2b / ell; }
+    if (scaled) { x2a = x2a / k.ell; x2b = x2b / k.ell; }
     double* o = out + (long)p * out_stride;
     const bool vec = two && ((n2 & 1) == 0) && ((reinterpret_cast<uintptr_t>(o) & 15) == 0);
-#pragma unroll
-    for (int rr = 0; rr < ASM_ROWS; ++rr) {
+    const int nr = min(ASM_ROWS, n1 - r0);
+#pragma unroll 4
+    for (int rr = 0; rr < nr; ++rr) {
         const int r = r0 + rr;
-        if (r >= n1) break;
-        double x1 = a1[r];
-        if (scaled) x1 = x1 / ell;
-        const double va = assemble_element(kind, sig2, ell, chi, ell2, r, c0, x1, x2a);
+        const double x1 = x1s[rr];
+        const double va = assemble_element<KIND>(k, r == c0, x1, x2a);
+        const double vb = assemble_element<KIND>(k, r == c0 + 1, x1, x2b);
         if (vec) {
-            const double vb = assemble_element(kind, sig2, ell, chi, ell2, r, c0 + 1, x1, x2b);
             *reinterpret_cast<double2*>(o + (long)r * n2 + c0) = make_double2(va, vb);
         } else {
             o[(long)r * n2 + c0] = va;
-            if (two) o[(long)r * n2 + c0 + 1] = assemble_element(kind, sig2, ell, chi, ell2, r, c0 + 1, x1, x2b);
+            if (two) o[(long)r * n2 + c0 + 1] = vb;
+        }
+    }
+}
+
+constexpr int SYM_T = 64;            // tile edge of the symmetric kernel
+constexpr int SYM_LD = SYM_T + 1;    // odd stride: conflict-free row and column access
+constexpr int SYM_SMEM = (2 * SYM_T * SYM_LD + 2 * SYM_T) * 8;   // 67584 B -> 3 CTAs / SM
+
+template <int KIND>
+__global__ void __launch_bounds__(NTHR)
+assemble_sym_kernel(const double* __restrict__ t, long t_stride, int n, const double* __restrict__ theta,
+                    double* __restrict__ out, long out_stride) {
+    extern __shared__ __align__(16) double dsm[];
+    double* S = dsm;
+    double* ST = dsm + SYM_T * SYM_LD;
+    double* xr = ST + SYM_T * SYM_LD;
+    double* xc = xr + SYM_T;
+    const int p = blockIdx.y, q = blockIdx.x;
+    int I = (int)((sqrt(8.0 * q + 1.0) - 1.0) * 0.5);
+    while ((I + 1) * (I + 2) / 2 <= q) ++I;
+    while (I * (I + 1) / 2 > q) --I;
+    const int J = q - I * (I + 1) / 2;
+    const AsmConsts k(theta + 3 * p);
+    constexpr bool scaled = AsmScaled<KIND>::value;
+    const double* a = t + (long)p * t_stride;
+    const int tid = threadIdx.x;
+    if (tid < 2 * SYM_T) {
+        const int idx = (tid < SYM_T ? I * SYM_T + tid : J * SYM_T + tid - SYM_T);
+        double v = idx < n ? a[idx] : 0.0;
+        if (scaled) v = v / k.ell;
+        (tid < SYM_T ? xr[tid] : xc[tid - SYM_T]) = v;
+    }
+    __syncthreads();
+    const int ty = tid >> 4, tx = tid & 15;
+    double x1[4], x2[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { x1[i] = xr[ty + 16 * i]; x2[i] = xc[tx + 16 * i]; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = ty + 16 * i, c = tx + 16 * j;
+            const double v = assemble_element<KIND>(k, I == J && r == c, x1[i], x2[j]);
+            S[r * SYM_LD + c] = v;
+            if (I != J) ST[c * SYM_LD + r] = (KIND == 4) ? -v : v;
+        }
+    __syncthreads();
+    double* o = out + (long)p * out_stride;
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int rr = warp; rr < SYM_T; rr += NTHR / 32) {
+        const int gr = I * SYM_T + rr;
+        if (gr < n) {
+#pragma unroll
+            for (int cc = lane; cc < SYM_T; cc += 32) {
+                const int gc = J * SYM_T + cc;
+                if (gc < n) o[(long)gr * n + gc] = S[rr * SYM_LD + cc];
+            }
+        }
+        const int hr = J * SYM_T + rr;
+        if (I != J && hr < n) {
+#pragma unroll
+            for (int cc = lane; cc < SYM_T; cc += 32) {
+                const int hc = I * SYM_T + cc;
+                if (hc < n) o[(long)hr * n + hc] = ST[rr * SYM_LD + cc];
+            }
         }
     }
 }

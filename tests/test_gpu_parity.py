@@ -152,6 +152,36 @@ def test_assemble_kinds(ctx, n1, n2):
             assert rel(got[p], ref) <= 1e-14, (kind, p)
 
 
+@pytest.mark.parametrize("n", [1, 63, 90, 257, 1000])
+def test_assemble_symmetric_path(ctx, n):
+    """t1 is t2 (same device pointer): the lower-triangle kernel that mirrors tiles through shared memory."""
+    import torch
+
+    rng = np.random.default_rng(n)
+    t = np.sort(rng.uniform(0, 1, n))
+    theta = np.log(np.array([[1.7, 0.07, 3e-3], [0.4, 0.004, 1e-2], [3.0, 1.5, 1e-6]]))   # incl. exp underflow
+    dev = torch.device("cuda", 0)
+    a, th = (torch.as_tensor(x, device=dev) for x in (t, theta))
+    out = torch.empty((3, n, n), dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    for kind in range(7):
+        out.fill_(float("nan"))
+        ctx.assemble_device(kind, a.data_ptr(), 0, n, a.data_ptr(), 0, n, th.data_ptr(), 3, out.data_ptr(), 0)
+        got = out.cpu().numpy()
+        for p in range(3):
+            s2, ell, chi = np.exp(theta[p])
+            d = t[:, None] - t[None, :]
+            kap = orc.np_rbf_eval(t, t, s2, ell)
+            dx2 = (t[:, None] / ell - t[None, :] / ell) ** 2
+            ref = {0: lambda: orc.np_kernel(t, theta[p]), 1: lambda: kap + np.diag(np.full(n, chi)),
+                   2: lambda: orc.np_kernel(t, theta[p], t2=t), 3: lambda: kap, 4: lambda: -d * kap / ell**2,
+                   5: lambda: (1 - (d**2 / ell**2)) * kap / ell**2,
+                   6: lambda: s2 * (np.exp(-0.5 * dx2) * dx2)}[kind]()
+            assert np.all(np.isfinite(got[p]))
+            # elementwise: 4 ulp relative, plus the flush-to-zero of results below 2^-1021 (fastmath.h)
+            assert np.all(np.abs(got[p] - ref) <= 1e-15 * np.abs(ref) + 1e-300 * max(1.0, np.abs(ref).max())), (kind, p)
+
+
 # ------------------------------------------------------------------ posterior moments
 @pytest.mark.parametrize("name", REAL_CONFIGS)
 def test_predict_and_lstsq_moments_golden(ctx, name):
