@@ -5,7 +5,7 @@
 // down to ~20 FP64-pipe instructions.  Both compile for host and device so tests/test_fastmath.py can
 // measure their error on the CPU (g++ -mfma) against long-double references.
 //
-//   gpbo_exp(x)          |error| < 1 ulp for -708 <= x <= 708.  Results below 2^-1021 (x < -708) are flushed to 0
+//   gpbo_exp(x)          |error| <= 1 ulp for -708 <= x <= 708.  Results below 2^-1021 (x < -708) are flushed to 0
 //                        (absolute error < 3.4e-308; the reference's np.exp returns sub-normals there);
 //                        x > 708 returns +inf, NaN returns NaN.
 //   gpbo_div(a, b, rb)   a / b for a divisor b whose correctly rounded reciprocal rb = 1/b is known;
