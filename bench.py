@@ -244,25 +244,41 @@ def main():
     h2d = Th.nbytes + Yh.nbytes + thh.nbytes + gph.nbytes
     d2h = B * (8 + 24 + 4)
 
-    # roofline of the dominant kernel (lauum_grad: K^-1 tiles + gradient traces), per launch
+    # roofline of the dominant kernel class, per launch: algorithmic flops = m_pad^3/3 per pair for each
+    # of potrf (diag+panel), trtri, lauum; "issued" = DMMA flops the 128-tile schedule actually executes.
     T_blocks = (m + 127) // 128
     m_pad = T_blocks * 128
+    blk = 2.0 * 128 ** 3
+    issued_pp = {
+        "chol_diag": blk * sum(j for j in range(T_blocks)),
+        "chol_panel": blk * sum((T_blocks - 1 - j) * (j + 1) for j in range(T_blocks)),
+        "trtri": blk * sum(i - j + 1 for i in range(1, T_blocks) for j in range(i)),
+        "lauum_grad": blk * sum((i + 1) * (T_blocks - i) for i in range(T_blocks)),
+    }
     dom = max(("chol_panel", "trtri", "lauum_grad"), key=lambda k: prof[k][0])
     cap = min(B, ctx.wave_capacity(m))
     waves = [min(cap, B - w0) for w0 in range(0, B, cap)]
-    flops_third = float(m_pad) ** 3 / 3.0            # each of potrf / trtri / lauum: m^3/3 flops per pair
+    flops_third = float(m_pad) ** 3 / 3.0
     launches_dom = max(prof[dom][1], 1)
     total_flops_dom = flops_third * B * args.steps   # all launches of that class over the timed region
-    achieved = total_flops_dom / (prof[dom][0] * 1e-3) / 1e12
-    all_tensor_ms = prof["chol_panel"][0] + prof["trtri"][0] + prof["lauum_grad"][0] + prof["chol_diag"][0]
+    dom_ms = prof[dom][0] + (prof["chol_diag"][0] if dom == "chol_panel" else 0.0)   # potrf = diag + panel
+    achieved = total_flops_dom / (dom_ms * 1e-3) / 1e12
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dom)
+    except Exception:
+        pass
     roofline = {
         "bound": "tensor", "kernel": dom, "achieved": achieved, "peak": dmma_peak, "unit": "TFLOP/s",
-        "frac": achieved / dmma_peak, "traffic": None,
+        "frac": achieved / dmma_peak, "traffic": traffic,
         "peak_source": "FP64 DMMA issue-rate micro-benchmark run in this process (gpbo_bench_dmma_peak); "
                        "MEASURED_PEAKS.json holds no FP64 figure",
-        "flops_per_launch": total_flops_dom / launches_dom, "avg_launch_ms": prof[dom][0] / launches_dom,
+        "flops_per_launch": total_flops_dom / launches_dom, "avg_launch_ms": dom_ms / launches_dom,
         "share_of_step": prof[dom][0] / sum(v[0] for v in prof.values()),
         "whole_eval_tflops": world * B * float(m) ** 3 / (ms_per_step * 1e-3) / 1e12,
+        "whole_eval_frac": B * float(m) ** 3 / (ms_per_step * 1e-3) / 1e12 / dmma_peak,
+        "dmma_issued_tflops": {k: issued_pp[k] * B * args.steps / (prof[k][0] * 1e-3) / 1e12
+                               for k in issued_pp if prof[k][0] > 0},
         "kernel_ms": {k: round(v[0], 3) for k, v in prof.items() if v[1]},
         "waves": waves,
     }
@@ -282,7 +298,9 @@ def main():
     }
 
     if rank == 0 and world == 1 and not args.no_fit_sample:
+        out["roofline_assembly"] = assembly_roofline(ctx, dev)
         out["fit_sample"] = fit_sample(ctx, m)
+        out["fit_reference_configs"] = fit_reference_configs(ctx)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(T, Y, theta)
     elif rank == 0:
@@ -312,6 +330,63 @@ def fit_sample(ctx, m, r=2, S=32):
     return {"modes": r, "starts": S, "m": m, "m_est": m, "fit_seconds": t_fit, "moments_seconds": t_mom,
             "fits_per_s": r / (t_fit + t_mom), "lml_grad_evals": res["evals"], "rounds": res["rounds"],
             "best_lml": (-funs.min(1)).tolist()}
+
+
+def assembly_roofline(ctx, dev, n=8192, B=8):
+    """HBM-write roofline of the stand-alone kernel-matrix assembly (train K, sklearn order): 8 B per element."""
+    import torch
+
+    peaks = measured_peaks() or {}
+    peak = float(peaks.get("hbm_gbs", 6543.1))
+    t = torch.sort(torch.rand(B, n, dtype=torch.float64, device=dev), dim=1).values.contiguous()
+    th = torch.log(torch.tensor([[1.5, 0.05, 1e-2]], dtype=torch.float64, device=dev)).repeat(B, 1).contiguous()
+    o = torch.empty((B, n, n), dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    res = {}
+    for name, kind, other in (("train_K_symmetric", 0, t), ("cross_K_general", 2, t.clone())):
+        args = (kind, t.data_ptr(), n, n, other.data_ptr(), n, n, th.data_ptr(), B, o.data_ptr(), stream.cuda_stream)
+        ctx.assemble_device(*args)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record(stream)
+        for _ in range(5):
+            ctx.assemble_device(*args)
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        gbs = 5 * B * n * n * 8 / (e0.elapsed_time(e1) * 1e-3) / 1e9
+        res[name] = {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                     "bytes_per_launch": B * n * n * 8, "shape": [B, n, n]}
+    res["peak_source"] = "MEASURED_PEAKS.json hbm_gbs (burst copy bandwidth)" if peaks else "fallback 6543.1 GB/s"
+    return res
+
+
+def fit_reference_configs(ctx):
+    """Full step2 fit (all 101 starts per GP, the reference's own start points) + posterior moments on the three
+    reference experiment configurations (tests/golden/*.npz), with the reference's CPU wall time recorded when the
+    fixtures were generated (8-core build container) beside it."""
+    out = {}
+    for name in ("seird_090_090_10_360", "heat_1_20_05_80_5", "euler_006_200_03_400_6"):
+        g = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"), allow_pickle=False)
+        T, Y, t_est = g["T"], g["Y"], g["t_est"]
+        G = T.shape[0]
+        bl = np.log(g["bounds"])
+        S = g["starts"].shape[1] + 1
+        starts = np.zeros((G, S, 3))
+        starts[:, 1:] = g["starts"]
+        gp_of = np.repeat(np.arange(G, dtype=np.int32), S)
+        t0 = time.perf_counter()
+        res = ctx.fit(T, Y, bl, starts.reshape(-1, 3), gp_of)
+        funs = np.where(np.isfinite(res["fun"]), res["fun"], np.inf).reshape(G, S)
+        best = res["theta"].reshape(G, S, 3)[np.arange(G), funs.argmin(1)]
+        ctx.lstsq_moments(T, Y, best, t_est)
+        ctx.predict(T, Y, best, t_est)
+        dt = time.perf_counter() - t0
+        lml = -funs.min(1)
+        out[name] = {"gps": int(G), "m": int(T.shape[1]), "m_est": int(t_est.size), "starts": int(S),
+                     "seconds": dt, "fits_per_s": G / dt, "lml_grad_evals": res["evals"], "rounds": res["rounds"],
+                     "max_rel_lml_gap_vs_reference": float(np.max((g["lml_opt"] - lml) / np.abs(g["lml_opt"]))),
+                     "reference_cpu_fit_seconds": float(np.sum(g["fit_seconds"]))}
+    return out
 
 
 def cpu_baseline(T, Y, theta, budget_s=20.0):

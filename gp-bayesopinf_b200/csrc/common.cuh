@@ -27,7 +27,6 @@ constexpr int NTHR = 256;         // 8 warps: 2 (rows) x 4 (cols), warp tile 64 
 constexpr int STAGE_DBL = TB * LDT;
 constexpr int MAIN_SMEM = NSTAGE * 2 * STAGE_DBL * 8;                 // 163840 B
 constexpr int EPI_SMEM = TB * LDS * 8 + NSTAGE * STAGE_DBL * 8;       // 217088 B
-constexpr int DIAG_SMEM = (TB * LDP + 2 * TB) * 8;                    // 134144 B
 constexpr int TILE_SMEM = EPI_SMEM > MAIN_SMEM ? EPI_SMEM : MAIN_SMEM;
 
 // Per (GP, start) pair hyper-parameters in natural units, produced by prep_pairs_kernel.

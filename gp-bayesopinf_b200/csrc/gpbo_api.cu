@@ -155,8 +155,6 @@ int set_kernel_attrs() {
     CUDA_TRY(cudaFuncSetAttribute(chol_panel_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(chol_panel_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(chol_panel_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
-    CUDA_TRY(cudaFuncSetAttribute(trsv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
-    CUDA_TRY(cudaFuncSetAttribute(trsv_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(trtri_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(lauum_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
@@ -188,8 +186,8 @@ int factor_wave(gpbo_ctx* c, cudaStream_t s, const MatArgs& a, const double* t_d
             });
         }
     }
-    launch(c, C_TRSV, s, [&] { trsv_fwd_kernel<<<nb, NTHR, DIAG_SMEM, s>>>(a, ypad, c->z.as<double>()); });
-    launch(c, C_TRSV, s, [&] { trsv_bwd_kernel<<<nb, NTHR, DIAG_SMEM, s>>>(a, c->z.as<double>(), c->alpha.as<double>()); });
+    launch(c, C_TRSV, s, [&] { trsv_fwd_kernel<<<nb, NTHR, 0, s>>>(a, ypad, c->z.as<double>()); });
+    launch(c, C_TRSV, s, [&] { trsv_bwd_kernel<<<nb, NTHR, 0, s>>>(a, c->z.as<double>(), c->alpha.as<double>()); });
     CUDA_TRY(cudaGetLastError());
     return GPBO_OK;
 }

@@ -96,55 +96,191 @@ __global__ void prep_pairs_kernel(const double* __restrict__ theta, const int* _
 // P (stride LDP) holds the symmetric block S on entry (lower part used).  On exit the lower part
 // holds L (S = L L^T), the strict upper part holds inv(L)^T, dinv[i] = 1 / L_ii.
 // Returns (to every thread) whether a non-positive pivot was met; *logsum gets sum_i log L_ii.
-__device__ __forceinline__ bool potf2_trtri_smem(double* P, double* dval, double* dinv, double* logsum_out) {
+//
+// Blocked right-looking algorithm with 32-wide panels:
+//   per panel  (1) chol32_block: the 32x32 diagonal block is factored (32 rank-1 steps, one barrier each) and
+//                  inverted (8 lanes per column) by all threads;
+//              (2) all warps: panel X = A * inv(L_kk)^T;   (3) all warps: trailing A22 -= X X^T (register tiles);
+//   then the off-diagonal blocks of inv(L) by block rows: W_ij = -W_ii * sum_k L_ik W_kj.
+// `scratch` needs PB*(PB+1) doubles during the factorisation and PB*(3*PB+1) during the inversion (re-used).
+constexpr int PB = 32;            // panel width
+constexpr int LDW = PB + 1;       // stride of the 32x32 inverse in scratch
+constexpr int LDG = 3 * PB + 1;   // stride of the G scratch of the inversion
+constexpr int POTF_SCRATCH = PB * LDG;   // >= PB*LDW + PB
+
+// All 256 threads: Cholesky of the 32x32 block at P[o..o+32)^2 (lower part, in place), its inverse W
+// (lower triangular) to Wd (stride LDW, zeros above the diagonal) and transposed into the strict upper part
+// of P, dinv[o+i] = 1 / L_ii.  `rsv` = PB doubles of scratch.  Returns (uniformly) whether a pivot was <= 0.
+//
+// Right-looking with unscaled columns (the column scaling by 1/sqrt(d_j) is applied once at the end), so a
+// step is: broadcast pivot -> rsqrt -> rank-1 update of <= 496 entries by 256 threads -> one barrier.
+__device__ __forceinline__ bool chol32_block(double* P, int o, double* Wd, double* dinv, double* rsv) {
     const int tid = threadIdx.x;
+    const int r = tid >> 3, c8 = tid & 7;                 // row of the block, column class
+    double* Pr = P + (o + r) * LDP + o;
     bool bad = false;
-    const int tr = tid >> 4, tcn = tid & 15;
-    for (int j = 0; j < TB; ++j) {
+    for (int j = 0; j < PB - 1; ++j) {
+        double d = P[(o + j) * LDP + o + j];
+        if (!(d > 0.0)) { bad = true; d = 1.0; }
+        const double rs = rsqrt(d);
+        if (tid == 0) rsv[j] = rs;
+        if (r > j) {
+            const double w = Pr[j] * (rs * rs);
+#pragma unroll
+            for (int q = 0; q < PB / 8; ++q) {
+                const int c = c8 + 8 * q;
+                if (c > j && c <= r) Pr[c] = fma(-w, P[(o + c) * LDP + o + j], Pr[c]);
+            }
+        }
         __syncthreads();
-        double d = P[j * LDP + j];
-        if (!(d > 0.0)) { bad = true; d = 1.0; }   // same value on every thread
-        if (tid == 0) dval[j] = d;
-        const double invd = 1.0 / d;
-        for (int r = j + 1 + tr; r < TB; r += 16) {
-            const double lr = P[r * LDP + j] * invd;
-            for (int c = j + 1 + tcn; c <= r; c += 16) P[r * LDP + c] -= lr * P[c * LDP + j];
+    }
+    {
+        double d = P[(o + PB - 1) * LDP + o + PB - 1];
+        if (!(d > 0.0)) { bad = true; d = 1.0; }
+        if (tid == 0) rsv[PB - 1] = rsqrt(d);
+    }
+    __syncthreads();
+    // scale: L_rc = a_rc * rs_c (c < r), L_cc = d_c * rs_c
+#pragma unroll
+    for (int q = 0; q < PB / 8; ++q) {
+        const int c = c8 + 8 * q;
+        if (c <= r) {
+            const double v = Pr[c];
+            Pr[c] = (c == r && !(v > 0.0)) ? 1.0 : v * rsv[c];
+        }
+    }
+    if (tid < PB) dinv[o + tid] = rsv[tid];               // 1 / L_ii = rs_i  (L_ii = d_i rs_i = sqrt(d_i))
+    __syncthreads();
+    // inverse: 8 lanes per column jc (tid>>3), forward substitution over rows; the k-sum is split over the 8 lanes
+    {
+        const int jc = tid >> 3, h = tid & 7;
+        const unsigned FULL = 0xffffffffu;
+        for (int rr = 0; rr < PB; ++rr) {
+            // warp-uniform loop; groups with rr <= jc only publish the known entries
+            double sacc = 0.0;
+            if (rr > jc) {
+                const double* Lr = P + (o + rr) * LDP + o;
+                for (int k = jc + h; k < rr; k += 8) sacc = fma(Lr[k], Wd[k * LDW + jc], sacc);
+            }
+            sacc += __shfl_xor_sync(FULL, sacc, 1);
+            sacc += __shfl_xor_sync(FULL, sacc, 2);
+            sacc += __shfl_xor_sync(FULL, sacc, 4);
+            if (h == 0) {
+                const double wv = (rr == jc) ? rsv[rr] : ((rr > jc) ? -sacc * rsv[rr] : 0.0);
+                Wd[rr * LDW + jc] = wv;
+                if (rr > jc) P[(o + jc) * LDP + o + rr] = wv;
+            }
+            __syncwarp();
         }
     }
     __syncthreads();
-    // scale columns: L_rc = S_rc / sqrt(d_c), L_cc = sqrt(d_c)
-    if (tid < TB) {
-        const int c = tid;
-        const double s = sqrt(dval[c]);
-        const double is = 1.0 / s;
-        for (int r = c + 1; r < TB; ++r) P[r * LDP + c] *= is;
-        P[c * LDP + c] = s;
-        dinv[c] = is;
+    return bad;
+}
+
+__device__ __forceinline__ bool potf2_trtri_smem(double* P, double* scratch, double* dinv, double* logsum_out) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    bool bad = false;
+    double* Wd = scratch;
+    double* rsv = scratch + PB * LDW;
+    for (int kb = 0; kb < TB / PB; ++kb) {
+        const int o = kb * PB;
+        bad |= chol32_block(P, o, Wd, dinv, rsv);
+        const int R0 = o + PB, n = TB - R0;
+        if (n <= 0) break;
+        // (2) panel: X[r][c] = sum_{k<=c} A[r][o+k] W[c][k]
+        {
+            const int rr = tid >> 3, cq = tid & 7;
+            double x[3][4];
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) x[t][q] = 0.0;
+                const int r = R0 + rr + 32 * t;
+                if (r < TB) {
+                    const double* Ar = P + r * LDP + o;
+#pragma unroll 16
+                    for (int k = 0; k < PB; ++k) {
+                        const double av = Ar[k];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) x[t][q] = fma(av, Wd[(cq + 8 * q) * LDW + k], x[t][q]);
+                    }
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                const int r = R0 + rr + 32 * t;
+                if (r < TB) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) P[r * LDP + o + cq + 8 * q] = x[t][q];
+                }
+            }
+            __syncthreads();
+        }
+        // (3) trailing update of the lower triangle: A[r][c] -= sum_k X[r][k] X[c][k]
+        {
+            const int ty = tid >> 4, tx = tid & 15;
+            const int nt = n >> 4;                 // 6, 4, 2
+            double acc[6][6];
+#pragma unroll
+            for (int ii = 0; ii < 6; ++ii)
+#pragma unroll
+                for (int jj = 0; jj < 6; ++jj) acc[ii][jj] = 0.0;
+            const double* Xr = P + (R0 + ty) * LDP + o;
+            const double* Xc = P + (R0 + tx) * LDP + o;
+#pragma unroll 4
+            for (int k = 0; k < PB; ++k) {
+                double xr[6], xc[6];
+#pragma unroll
+                for (int ii = 0; ii < 6; ++ii) {
+                    xr[ii] = ii < nt ? Xr[ii * 16 * LDP + k] : 0.0;
+                    xc[ii] = ii < nt ? Xc[ii * 16 * LDP + k] : 0.0;
+                }
+#pragma unroll
+                for (int ii = 0; ii < 6; ++ii)
+#pragma unroll
+                    for (int jj = 0; jj <= ii; ++jj) acc[ii][jj] = fma(xr[ii], xc[jj], acc[ii][jj]);
+            }
+#pragma unroll
+            for (int ii = 0; ii < 6; ++ii)
+#pragma unroll
+                for (int jj = 0; jj <= ii; ++jj) {
+                    const int r = R0 + ty + 16 * ii, c = R0 + tx + 16 * jj;
+                    if (ii < nt && c <= r) P[r * LDP + c] -= acc[ii][jj];
+                }
+        }
+        __syncthreads();
     }
-    __syncthreads();
+    // off-diagonal blocks of W = inv(L), block row bi; W stored transposed in the strict upper part of P
+    double* Gs = scratch;
+    for (int bi = 1; bi < TB / PB; ++bi) {
+        const int oi = bi * PB, ncol = oi;
+        const int r = oi + lane;
+        const double* Lr = P + r * LDP;
+        for (int col = warp; col < ncol; col += NTHR / 32) {
+            const double* Wc = P + col * LDP;            // Wc[k] = W[k][col] for k > col
+            double g = Lr[col] * dinv[col];
+            for (int k = col + 1; k < oi; ++k) g = fma(Lr[k], Wc[k], g);
+            Gs[lane * LDG + col] = g;
+        }
+        __syncthreads();
+        for (int col = warp; col < ncol; col += NTHR / 32) {
+            double acc = dinv[r] * Gs[lane * LDG + col];
+            for (int ap = 0; ap < PB; ++ap) {
+                // W_ii[lane][ap] for ap < lane is stored at P[oi+ap][oi+lane]
+                const double wv = P[(oi + ap) * LDP + r];
+                const double gv = Gs[ap * LDG + col];
+                if (ap < lane) acc = fma(wv, gv, acc);
+            }
+            P[col * LDP + r] = -acc;
+        }
+        __syncthreads();
+    }
     if (tid < 32) {
         double ls = 0.0;
         for (int c = tid; c < TB; c += 32) ls += log(P[c * LDP + c]);
         ls = warp_sum(ls);
         if (tid == 0) *logsum_out = ls;
-    }
-    // inverse, two threads per column (even / odd k), X[k][c] kept at P[c][k] (k > c)
-    {
-        const int c = tid >> 1, h = tid & 1;
-        double* xrow = P + c * LDP;
-        const double xc = dinv[c];
-        // warp-uniform trip count (columns of one warp are 16 consecutive c): lanes with i <= c idle
-        for (int i = (tid >> 5) * 16 + 1; i < TB; ++i) {
-            const double* Li = P + i * LDP;
-            double s = 0.0;
-            if (i > c) {
-                if (h == 0) s = Li[c] * xc;
-                for (int k = c + 1 + h; k < i; k += 2) s += Li[k] * xrow[k];
-            }
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            if (h == 0 && i > c) xrow[i] = -s * dinv[i];
-            __syncwarp();
-        }
     }
     __syncthreads();
     return bad;
@@ -169,8 +305,8 @@ __global__ void __launch_bounds__(NTHR, 1) chol_diag_kernel(MatArgs a, int j) {
     __syncthreads();   // every warp is done with the ring: its memory becomes P
 
     double* P = smem;
-    double* dval = smem + TB * LDP;
-    double* dinv = dval + TB;
+    double* dinv = smem + TB * LDP;
+    double* scratch = dinv + TB;
     __shared__ double logsum;
     {
         const PairParams q = a.pp[p];
@@ -192,7 +328,7 @@ __global__ void __launch_bounds__(NTHR, 1) chol_diag_kernel(MatArgs a, int j) {
                         P[r * LDP + c] = el(j * TB + r, j * TB + c, xr[mi], xc[ni][e]) - acc.v[mi][ni][e];
                 }
     }
-    const bool bad = potf2_trtri_smem(P, dval, dinv, &logsum);
+    const bool bad = potf2_trtri_smem(P, scratch, dinv, &logsum);
 
     // write L_jj (lower), D_j = inv(L_jj) and DT_j = D_j^T
     double* Lout = Ap + (long)j * TB * a.lda + j * TB;
@@ -298,11 +434,11 @@ chol_panel_kernel(MatArgs a, int j, double* X, long x_stride, int xT, CrossArgs 
 }
 
 // ---- forward / backward substitution with the block factor ------------------------------
+// The diagonal-block solves use the block inverses D_j = inv(L_jj) (a 128x128 GEMV each) like the panel
+// TRSM does, instead of a 128-step sequential substitution.
 // z = L^-1 y (one CTA per pair).  _gpr.py:601 (cho_solve, first half).
 __global__ void __launch_bounds__(NTHR, 1) trsv_fwd_kernel(MatArgs a, const double* __restrict__ ypad, double* z) {
-    extern __shared__ __align__(16) double smem[];
-    double* Lb = smem;                 // 128 x LDP
-    double* xs = smem + TB * LDP;      // 128
+    __shared__ double xs[TB];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int p = blockIdx.x;
     const double* Ap = a.A + (long)p * a.mat_stride;
@@ -324,20 +460,19 @@ __global__ void __launch_bounds__(NTHR, 1) trsv_fwd_kernel(MatArgs a, const doub
             s = warp_sum(s);
             if (lane == 0) xs[r] = yp[jb * TB + r] - s;
         }
-        // stage L_jj (lower part)
-        for (int q = tid; q < TB * TB; q += NTHR) {
-            const int r = q >> 7, c = q & 127;
-            if (c <= r) Lb[r * LDP + c] = rows[(long)r * a.lda + jb * TB + c];
-        }
         __syncthreads();
-        if (tid < TB) {
-            double rk = xs[tid];
-            for (int i = 0; i < TB; ++i) {
-                if (tid == i) xs[i] = rk / Lb[i * LDP + i];
-                asm volatile("bar.sync 1, 128;\n" ::);
-                if (tid > i) rk -= Lb[tid * LDP + i] * xs[i];
+        // z_j = D_j r  (D_j lower triangular)
+        const double* Dj = a.D + ((long)p * a.T + jb) * (TB * TB);
+        for (int rr = 0; rr < 16; ++rr) {
+            const int r = warp * 16 + rr;
+            double s = 0.0;
+#pragma unroll
+            for (int q = 0; q < TB / 32; ++q) {
+                const int c = lane + 32 * q;
+                if (c <= r) s = fma(Dj[r * TB + c], xs[c], s);
             }
-            zp[jb * TB + tid] = xs[tid];
+            s = warp_sum(s);
+            if (lane == 0) zp[jb * TB + r] = s;
         }
         __syncthreads();
     }
@@ -345,10 +480,8 @@ __global__ void __launch_bounds__(NTHR, 1) trsv_fwd_kernel(MatArgs a, const doub
 
 // alpha = L^-T z (one CTA per pair).  _gpr.py:601 (cho_solve, second half).
 __global__ void __launch_bounds__(NTHR, 1) trsv_bwd_kernel(MatArgs a, const double* __restrict__ z, double* alpha) {
-    extern __shared__ __align__(16) double smem[];
-    double* Lb = smem;
-    double* xs = smem + TB * LDP;
-    const int tid = threadIdx.x;
+    __shared__ double xs[TB], ws[TB];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int p = blockIdx.x;
     const double* Ap = a.A + (long)p * a.mat_stride;
     const double* zp = z + (long)p * a.lda;
@@ -357,19 +490,20 @@ __global__ void __launch_bounds__(NTHR, 1) trsv_bwd_kernel(MatArgs a, const doub
     __syncthreads();
     for (int jb = a.T - 1; jb >= 0; --jb) {
         const double* rows = Ap + (long)jb * TB * a.lda;
-        for (int q = tid; q < TB * TB; q += NTHR) {
-            const int r = q >> 7, c = q & 127;
-            if (c <= r) Lb[r * LDP + c] = rows[(long)r * a.lda + jb * TB + c];
-        }
+        if (tid < TB) ws[tid] = wp[jb * TB + tid];
         __syncthreads();
-        if (tid < TB) {
-            double wk = wp[jb * TB + tid];
-            for (int i = TB - 1; i >= 0; --i) {
-                if (tid == i) xs[i] = wk / Lb[i * LDP + i];
-                asm volatile("bar.sync 1, 128;\n" ::);
-                if (tid < i) wk -= Lb[i * LDP + tid] * xs[i];
+        // alpha_j = inv(L_jj)^T w_j = DT_j w_j  (DT_j upper triangular, rows contiguous)
+        const double* DTj = a.DT + ((long)p * a.T + jb) * (TB * TB);
+        for (int rr = 0; rr < 16; ++rr) {
+            const int r = warp * 16 + rr;
+            double s = 0.0;
+#pragma unroll
+            for (int q = 0; q < TB / 32; ++q) {
+                const int c = lane + 32 * q;
+                if (c >= r) s = fma(DTj[r * TB + c], ws[c], s);
             }
-            wp[jb * TB + tid] = xs[tid];
+            s = warp_sum(s);
+            if (lane == 0) { xs[r] = s; wp[jb * TB + r] = s; }
         }
         __syncthreads();
         // w[0:nk] -= L[j, 0:nk]^T alpha_j ; threads across k (coalesced rows)
