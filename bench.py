@@ -105,8 +105,10 @@ def run_reference(args):
         return
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import gp_oracle as orc
-    from threadpoolctl import threadpool_info
+    from threadpoolctl import threadpool_info, threadpool_limits
 
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host core the BLAS can take
+    threadpool_limits(limits=os.cpu_count())
     T, Y, theta, gp_of = workload(R_MODES, N_POINTS, N_STARTS)
     b = np.array([(1e-5, 1e5), (1e-5, 1e2), (1e-16, 1e2)])
     gp = orc.OracleGP(tuple(b[0]), tuple(b[1]), tuple(b[2]), 0)
@@ -393,8 +395,9 @@ def cpu_baseline(T, Y, theta, budget_s=20.0):
     """Oracle port (sklearn-driven, as the reference) timed on this box's host cores, bounded sample."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import gp_oracle as orc
-    from threadpoolctl import threadpool_info
+    from threadpoolctl import threadpool_info, threadpool_limits
 
+    threadpool_limits(limits=os.cpu_count())
     b = np.array([(1e-5, 1e5), (1e-5, 1e2), (1e-16, 1e2)])
     gp = orc.OracleGP(tuple(b[0]), tuple(b[1]), tuple(b[2]), 0)
     gp.gpr.optimizer = None

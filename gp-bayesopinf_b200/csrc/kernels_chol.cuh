@@ -182,6 +182,7 @@ __device__ __forceinline__ bool potf2_trtri_smem(double* P, double* scratch, dou
     bool bad = false;
     double* Wd = scratch;
     double* rsv = scratch + PB * LDW;
+    __syncthreads();   // P was just filled by all threads
     for (int kb = 0; kb < TB / PB; ++kb) {
         const int o = kb * PB;
         bad |= chol32_block(P, o, Wd, dinv, rsv);

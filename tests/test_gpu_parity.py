@@ -112,6 +112,26 @@ def test_ragged_batch_many_pairs_waves(ctx):
         assert abs(big[0][k] - l0) <= 1e-10 * abs(l0)
 
 
+def test_replicated_pairs_are_bitwise_identical(ctx):
+    """Race detector: 600 copies of one (GP, theta) pair spread over the SMs must give bit-identical results
+    (all reductions are deterministic), equal to the oracle, with every status 0."""
+    t, y = orc.synthetic_trajectories(1, 333, seed=5)
+    th = np.log([1.9, 0.06, 4e-3])
+    B = 600
+    lml, grad, st = ctx.lml_grad(t[None], y, np.tile(th, (B, 1)), np.zeros(B, dtype=np.int32))
+    assert np.all(st == 0)
+    assert np.all(lml == lml[0]) and np.all(grad == grad[0])
+    l0, g0, _ = orc.np_lml_grad(t, y[0], th)
+    assert abs(lml[0] - l0) <= 1e-10 * abs(l0)
+    assert rel(grad[0], g0, max(1.0, np.abs(g0).max())) <= 1e-9
+    # same for the posterior-moment path
+    t_est = np.linspace(0, 1, 150)
+    G = 160
+    state, ddt, cov, st2 = ctx.lstsq_moments(np.tile(t, (G, 1)), np.tile(y, (G, 1)), np.tile(th, (G, 1)), t_est)
+    assert np.all(st2 == 0)
+    assert np.all(state == state[0]) and np.all(ddt == ddt[0]) and np.all(cov == cov[0])
+
+
 # ------------------------------------------------------------------ assembly
 @pytest.mark.parametrize("n1,n2", [(90, 90), (257, 33), (400, 200)])
 def test_assemble_kinds(ctx, n1, n2):
