@@ -303,6 +303,7 @@ def main():
         out["roofline_assembly"] = assembly_roofline(ctx, dev)
         out["fit_sample"] = fit_sample(ctx, m)
         out["fit_reference_configs"] = fit_reference_configs(ctx)
+        out["moments_sample"] = moments_sample(ctx, m)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(T, Y, theta)
     elif rank == 0:
@@ -389,6 +390,30 @@ def fit_reference_configs(ctx):
                      "max_rel_lml_gap_vs_reference": float(np.max((g["lml_opt"] - lml) / np.abs(g["lml_opt"]))),
                      "reference_cpu_fit_seconds": float(np.sum(g["fit_seconds"]))}
     return out
+
+
+def moments_sample(ctx, m, G=8):
+    """compute_lstsq_matrices for G GPs at m = m' (state, ddt, ddt covariance, sqrtW by Newton-Schulz): host-call wall
+    time (includes the D2H of two m'^2 matrices per GP) and per-class device milliseconds."""
+    T, Y, _, _ = workload(G, m, 1, seed=321)
+    theta = np.tile(np.log([1.5, 0.05, 1e-2]), (G, 1))
+    t_est = np.linspace(0, 1, m)
+    ctx.lstsq_weights(T[:1], Y[:1], theta[:1], t_est, 1e-8)          # warm-up / allocation
+    ctx.profile_enable(True)
+    t0 = time.perf_counter()
+    state, ddt, cov, w, st, wst, wit = ctx.lstsq_weights(T, Y, theta, t_est, 1e-8)
+    dt = time.perf_counter() - t0
+    prof = ctx.profile_get()
+    ctx.profile_enable(False)
+    A = cov[0] + 1e-8 * np.eye(m)
+    x = np.random.default_rng(0).standard_normal(m)
+    resid = float(np.abs(w[0] @ (A @ (w[0] @ x)) - x).max() / np.abs(x).max())     # sqrtW (C + eta I) sqrtW x = x
+    T_blocks = (m + 127) // 128
+    ns_flops = float(wit.max() + 1) * G * 2.0 * 128 ** 3 * T_blocks * (T_blocks ** 2 + T_blocks * (T_blocks + 1))
+    return {"gps": G, "m": m, "m_est": m, "seconds": dt, "device_ms": {k: round(v[0], 3) for k, v in prof.items() if v[1]},
+            "sqrtw_iterations": int(wit.max()), "sqrtw_status_ok": int((wst == 0).sum()),
+            "sqrtw_identity_residual": resid,
+            "sqrtw_dmma_issued_tflops": ns_flops / (prof["sqrtw"][0] * 1e-3) / 1e12 if prof["sqrtw"][0] > 0 else None}
 
 
 def cpu_baseline(T, Y, theta, budget_s=20.0):

@@ -15,15 +15,16 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgpbo.so")
 
-NCLASS = 11
+NCLASS = 12
 KERNEL_CLASSES = ("prep", "chol_diag", "chol_panel", "trsv", "trtri", "lauum_grad", "finalize",
-                  "cross_panel", "schur", "mean_std", "assemble")
+                  "cross_panel", "schur", "mean_std", "assemble", "sqrtw")
 
 EXPORTS = (
     "gpbo_version", "gpbo_last_error", "gpbo_create", "gpbo_destroy", "gpbo_launch_count",
     "gpbo_wave_capacity", "gpbo_assemble", "gpbo_lml_grad", "gpbo_lml_grad_host", "gpbo_fit_host",
     "gpbo_predict_host", "gpbo_lstsq_moments_host", "gpbo_lstsq_moments", "gpbo_profile_enable",
-    "gpbo_profile_get", "gpbo_bench_dmma_peak", "gpbo_lbfgsb_minimize",
+    "gpbo_profile_get", "gpbo_bench_dmma_peak", "gpbo_lbfgsb_minimize", "gpbo_sqrtw", "gpbo_sqrtw_host",
+    "gpbo_lstsq_weights_host",
 )
 
 
@@ -64,6 +65,10 @@ def load():
     lib.gpbo_predict_host.argtypes = [vp, dp, dp, C.c_int, C.c_int, dp, dp, C.c_long, C.c_int, dp, dp, dp, ip]
     lib.gpbo_lstsq_moments_host.argtypes = [vp, dp, dp, C.c_int, C.c_int, dp, dp, C.c_long, C.c_int, dp, dp, dp, ip]
     lib.gpbo_lstsq_moments.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, vp, C.c_long, C.c_int, vp, vp, vp, vp, vp]
+    lib.gpbo_sqrtw.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, vp, ip, ip, vp]
+    lib.gpbo_sqrtw_host.argtypes = [vp, dp, C.c_int, C.c_int, C.c_double, dp, ip, ip]
+    lib.gpbo_lstsq_weights_host.argtypes = [vp, dp, dp, C.c_int, C.c_int, dp, dp, C.c_long, C.c_int, C.c_double, dp, dp,
+                                            dp, dp, ip, ip, ip]
     lib.gpbo_profile_enable.argtypes = [vp, C.c_int]
     lib.gpbo_profile_get.argtypes = [vp, dp, C.POINTER(C.c_longlong)]
     lib.gpbo_bench_dmma_peak.argtypes = [vp, C.c_int, dp, dp]
@@ -214,6 +219,36 @@ class Context:
         _check(self._lib.gpbo_lstsq_moments_host(self._h, _dp(t), _dp(y), G, m, _dp(theta), _dp(pts), stride, n,
                                                  _dp(state), _dp(ddt), _dp(cov), _ip(st)), "gpbo_lstsq_moments_host")
         return state, ddt, cov, st
+
+    def sqrtw(self, cov, eta):
+        """sqrtW = (C + eta I)^(-1/2) for a stack of covariances (G, n, n).  -> sqrtw, status, iters."""
+        cov = _f64(cov)
+        if cov.ndim == 2:
+            cov = cov[None]
+        G, n, n2 = cov.shape
+        if n != n2:
+            raise ValueError("sqrtw: covariance must be square")
+        out = np.empty_like(cov)
+        st = np.empty(G, dtype=np.int32)
+        it = np.empty(G, dtype=np.int32)
+        _check(self._lib.gpbo_sqrtw_host(self._h, _dp(cov), G, n, float(eta), _dp(out), _ip(st), _ip(it)),
+               "gpbo_sqrtw_host")
+        return out, st, it
+
+    def lstsq_weights(self, t, y, theta, t_est, eta):
+        """state, ddt, cov AND sqrtW in one call (the covariance never leaves HBM in between).
+        -> state, ddt, cov, sqrtw, status, w_status, w_iters."""
+        t, y = _f64(np.atleast_2d(t)), _f64(np.atleast_2d(y))
+        G, m = t.shape
+        theta = _f64(np.atleast_2d(theta))
+        pts, stride, n = self._points(t_est, G)
+        state, ddt = np.empty((G, n)), np.empty((G, n))
+        cov, w = np.empty((G, n, n)), np.empty((G, n, n))
+        st, wst, wit = (np.empty(G, dtype=np.int32) for _ in range(3))
+        _check(self._lib.gpbo_lstsq_weights_host(self._h, _dp(t), _dp(y), G, m, _dp(theta), _dp(pts), stride, n,
+                                                 float(eta), _dp(state), _dp(ddt), _dp(cov), _dp(w), _ip(st), _ip(wst),
+                                                 _ip(wit)), "gpbo_lstsq_weights_host")
+        return state, ddt, cov, w, st, wst, wit
 
     # -- device-pointer entry points (torch tensors are only address carriers) ------------
     def assemble_device(self, kind, t1_ptr, t1_stride, n1, t2_ptr, t2_stride, n2, theta_ptr, B, out_ptr, stream=0):

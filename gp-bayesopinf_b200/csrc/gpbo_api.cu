@@ -3,11 +3,13 @@
 #include "../../include/gpbo.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "kernels_predict.cuh"
+#include "kernels_sqrtw.cuh"
 #include "lbfgsb.h"
 
 using namespace gpbo;
@@ -62,6 +64,8 @@ struct gpbo_ctx {
     DevBuf t_dev, y_dev, ypad, theta_dev, gpof_dev, lml_dev, grad_dev, st_dev;
     // prediction
     DevBuf X, trow, tsrc, out1, out2, cov_dev;
+    // sqrtW (Newton-Schulz)
+    DevBuf nsY, nsZ, nsT, nsTT, nsYn, nsZn, nsPart, nsNorm, nsResid, w_dev;
     // pinned staging for the optimiser rounds
     double* h_theta = nullptr; double* h_lml = nullptr; double* h_grad = nullptr; int* h_gpof = nullptr;
     size_t h_cap = 0;
@@ -69,7 +73,7 @@ struct gpbo_ctx {
 
 namespace {
 
-enum { C_PREP = 0, C_DIAG, C_PANEL, C_TRSV, C_TRTRI, C_LAUUM, C_FINAL, C_CROSS, C_SCHUR, C_MEAN, C_ASM };
+enum { C_PREP = 0, C_DIAG, C_PANEL, C_TRSV, C_TRTRI, C_LAUUM, C_FINAL, C_CROSS, C_SCHUR, C_MEAN, C_ASM, C_SQRTW };
 
 template <class F>
 inline void launch(gpbo_ctx* c, int cls, cudaStream_t s, F&& f) {
@@ -158,6 +162,7 @@ int set_kernel_attrs() {
     CUDA_TRY(cudaFuncSetAttribute(trtri_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(lauum_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(ns_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
 #define GPBO_SYM_ATTR(K) CUDA_TRY(cudaFuncSetAttribute(assemble_sym_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, SYM_SMEM));
     GPBO_SYM_ATTR(0) GPBO_SYM_ATTR(1) GPBO_SYM_ATTR(2) GPBO_SYM_ATTR(3) GPBO_SYM_ATTR(4) GPBO_SYM_ATTR(5) GPBO_SYM_ATTR(6)
 #undef GPBO_SYM_ATTR
@@ -247,6 +252,94 @@ int lml_grad_device(gpbo_ctx* c, cudaStream_t s, const double* t, const double* 
     return GPBO_OK;
 }
 
+// sqrtW = (C + eta I)^(-1/2) for G matrices (device pointers); status / iters are HOST arrays (may be NULL).
+int sqrtw_device(gpbo_ctx* c, cudaStream_t s, const double* cov, int G, int n, double eta, double* out, int* status,
+                 int* iters) {
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc = set_kernel_attrs();
+    if (rc) return rc;
+    rc = resolve_limit(c);
+    if (rc) return rc;
+    const int ld = pad_to_tile(n), T = ld / TB, ntiles = T * (T + 1) / 2;
+    const size_t mat = (size_t)ld * ld * 8;
+    const int nfull = T * T;
+    const size_t per = 6 * mat + (size_t)nfull * 8 + 64;
+    // memory still free + what the Newton-Schulz buffers already hold; the factorisation waves are dropped
+    // if that is what it takes to fit one matrix
+    auto avail = [&]() -> size_t {
+        size_t fr = 0, tot = 0;
+        if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) return 0;
+        const size_t held = c->nsY.bytes + c->nsZ.bytes + c->nsT.bytes + c->nsTT.bytes + c->nsYn.bytes + c->nsZn.bytes;
+        return (size_t)(0.9 * (double)fr) + held;
+    };
+    size_t av = avail();
+    if (av < (size_t)std::min(G, 8) * per) {
+        CUDA_TRY(cudaStreamSynchronize(s));
+        c->A.release(); c->X.release(); c->D.release(); c->DT.release();
+        av = avail();
+    }
+    if (av < per) return fail(GPBO_ENOMEM, "sqrtw: one matrix does not fit in device memory");
+    int cap = (int)std::min<size_t>((size_t)G, av / per);
+    CUDA_TRY(c->nsY.ensure(cap * mat));
+    CUDA_TRY(c->nsZ.ensure(cap * mat));
+    CUDA_TRY(c->nsT.ensure(cap * mat));
+    CUDA_TRY(c->nsTT.ensure(cap * mat));
+    CUDA_TRY(c->nsYn.ensure(cap * mat));
+    CUDA_TRY(c->nsZn.ensure(cap * mat));
+    CUDA_TRY(c->nsPart.ensure((size_t)cap * nfull * 8));
+    CUDA_TRY(c->nsNorm.ensure((size_t)cap * 8));
+    CUDA_TRY(c->nsResid.ensure((size_t)cap * 8));
+    const int maxit = 90;
+    const bool debug_ns = std::getenv("GPBO_DEBUG_NS") != nullptr;
+    std::vector<double> resid(cap), prev(cap);
+    std::vector<char> done(cap);
+    for (int w0 = 0; w0 < G; w0 += cap) {
+        const int nb = std::min(cap, G - w0);
+        const double* Cw = cov + (size_t)w0 * n * n;
+        NsArgs a;
+        a.Y = c->nsY.as<double>(); a.Z = c->nsZ.as<double>(); a.T = c->nsT.as<double>(); a.TT = c->nsTT.as<double>();
+        a.Yn = c->nsYn.as<double>(); a.Zn = c->nsZn.as<double>();
+        a.stride = (long)ld * ld; a.ld = ld; a.n = n; a.part = c->nsPart.as<double>();
+        unsigned long long* norm = c->nsNorm.as<unsigned long long>();
+        CUDA_TRY(cudaMemsetAsync(norm, 0, (size_t)nb * 8, s));
+        launch(c, C_SQRTW, s, [&] { ns_norm_kernel<<<dim3((n + 7) / 8, nb), NTHR, 0, s>>>(Cw, n, eta, norm); });
+        launch(c, C_SQRTW, s, [&] { ns_init_kernel<<<dim3(ld, nb), NTHR, 0, s>>>(Cw, n, eta, norm, a); });
+        for (int p = 0; p < nb; ++p) { done[p] = 0; prev[p] = HUGE_VAL; if (status) status[w0 + p] = 0; if (iters) iters[w0 + p] = maxit; }
+        for (int it = 0; it < maxit; ++it) {
+            launch(c, C_SQRTW, s, [&] { ns_gemm_kernel<<<dim3(nb * nfull, 1), NTHR, MAIN_SMEM, s>>>(a, nfull, 0); });
+            launch(c, C_SQRTW, s, [&] { ns_resid_kernel<<<nb, NTHR, 0, s>>>(a.part, nfull, c->nsResid.as<double>()); });
+            CUDA_TRY(cudaMemcpyAsync(resid.data(), c->nsResid.p, (size_t)nb * 8, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(cudaStreamSynchronize(s));
+            bool all_done = true;
+            if (debug_ns) std::fprintf(stderr, "[gpbo sqrtw] it %d r0 %.6e\n", it, std::sqrt(resid[0]));
+            for (int p = 0; p < nb; ++p) {
+                if (done[p]) continue;
+                const double r = std::sqrt(resid[p]);
+                if (!std::isfinite(r)) {                       // an eigenvalue <= 0 made Z blow up
+                    done[p] = 2;
+                } else if (r <= 1e-11 * std::sqrt((double)ld) || (prev[p] < 0.05 && r >= 0.25 * prev[p])) {
+                    // converged; second test: the quadratic phase (r_k ~ r_{k-1}^2) has stalled at the rounding
+                    // floor ~ cond * eps -- the reference's eigh result is no more accurate there
+                    done[p] = 1;
+                    if (iters) iters[w0 + p] = it;
+                }
+                prev[p] = r;
+                if (!done[p]) all_done = false;
+            }
+            if (all_done) break;
+            launch(c, C_SQRTW, s, [&] { ns_gemm_kernel<<<dim3(nb * ntiles, 2), NTHR, MAIN_SMEM, s>>>(a, ntiles, 1); });
+            std::swap(a.Y, a.Yn);
+            std::swap(a.Z, a.Zn);
+        }
+        for (int p = 0; p < nb; ++p)
+            if (done[p] != 1 && status) status[w0 + p] = 1;
+        launch(c, C_SQRTW, s, [&] { ns_out_kernel<<<dim3(n, nb), NTHR, 0, s>>>(a, norm, out + (size_t)w0 * n * n); });
+        CUDA_TRY(cudaGetLastError());
+    }
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return GPBO_OK;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
@@ -277,7 +370,8 @@ int gpbo_destroy(gpbo_ctx* c) {
     cudaDeviceSynchronize();
     DevBuf* bufs[] = {&c->A, &c->D, &c->DT, &c->ts, &c->z, &c->alpha, &c->pp, &c->logdet, &c->part, &c->status,
                       &c->t_dev, &c->y_dev, &c->ypad, &c->theta_dev, &c->gpof_dev, &c->lml_dev, &c->grad_dev, &c->st_dev,
-                      &c->X, &c->trow, &c->tsrc, &c->out1, &c->out2, &c->cov_dev};
+                      &c->X, &c->trow, &c->tsrc, &c->out1, &c->out2, &c->cov_dev,
+                      &c->nsY, &c->nsZ, &c->nsT, &c->nsTT, &c->nsYn, &c->nsZn, &c->nsPart, &c->nsNorm, &c->nsResid, &c->w_dev};
     for (DevBuf* b : bufs) b->release();
     for (auto& r : c->recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     if (c->h_theta) cudaFreeHost(c->h_theta);
@@ -602,7 +696,8 @@ static int moments_device(gpbo_ctx* c, cudaStream_t s, int mode, const double* t
 
 static int moments_host(gpbo_ctx* c, int mode, const double* t, const double* y, int G, int m, const double* theta,
                         const double* pts, long pts_stride, int n, double* o1, double* o2, double* cov, double* alpha,
-                        int* status) {
+                        int* status, double eta = 0.0, double* sqrtw = nullptr, int* w_status = nullptr,
+                        int* w_iters = nullptr) {
     if (!c || !t || !y || !theta || !pts || !o1 || !o2 || G <= 0 || m <= 0 || n <= 0)
         return fail(GPBO_EINVAL, "moments_host: bad argument");
     CUDA_TRY(cudaSetDevice(c->device));
@@ -624,6 +719,13 @@ static int moments_host(gpbo_ctx* c, int mode, const double* t, const double* y,
                         cov ? c->cov_dev.as<double>() : nullptr, alpha ? c->grad_dev.as<double>() : nullptr,
                         c->st_dev.as<int>());
     if (rc) return rc;
+    if (sqrtw) {
+        if (!cov) return fail(GPBO_EINVAL, "lstsq_weights: cov output is required when sqrtw is requested");
+        CUDA_TRY(c->w_dev.ensure((size_t)G * n * n * 8));
+        rc = sqrtw_device(c, s, c->cov_dev.as<double>(), G, n, eta, c->w_dev.as<double>(), w_status, w_iters);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(sqrtw, c->w_dev.p, (size_t)G * n * n * 8, cudaMemcpyDeviceToHost, s));
+    }
     CUDA_TRY(cudaMemcpyAsync(o1, c->out1.p, (size_t)G * n * 8, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(o2, c->out2.p, (size_t)G * n * 8, cudaMemcpyDeviceToHost, s));
     if (cov) CUDA_TRY(cudaMemcpyAsync(cov, c->cov_dev.p, (size_t)G * n * n * 8, cudaMemcpyDeviceToHost, s));
@@ -643,6 +745,35 @@ int gpbo_lstsq_moments_host(gpbo_ctx* c, const double* t, const double* y, int G
                             const double* t_est, long test_stride, int n_est, double* state, double* ddt, double* cov,
                             int* status) {
     return moments_host(c, 1, t, y, G, m, theta, t_est, test_stride, n_est, state, ddt, cov, nullptr, status);
+}
+
+int gpbo_lstsq_weights_host(gpbo_ctx* c, const double* t, const double* y, int G, int m, const double* theta,
+                            const double* t_est, long test_stride, int n_est, double eta, double* state, double* ddt,
+                            double* cov, double* sqrtw, int* status, int* w_status, int* w_iters) {
+    if (!sqrtw || !cov) return fail(GPBO_EINVAL, "lstsq_weights_host: cov and sqrtw outputs are required");
+    return moments_host(c, 1, t, y, G, m, theta, t_est, test_stride, n_est, state, ddt, cov, nullptr, status, eta, sqrtw,
+                        w_status, w_iters);
+}
+
+int gpbo_sqrtw(gpbo_ctx* c, const double* cov, int G, int n, double eta, double* sqrtw, int* status, int* iters,
+               void* stream) {
+    if (!c || !cov || !sqrtw || G <= 0 || n <= 0) return fail(GPBO_EINVAL, "sqrtw: bad argument");
+    return sqrtw_device(c, static_cast<cudaStream_t>(stream), cov, G, n, eta, sqrtw, status, iters);
+}
+
+int gpbo_sqrtw_host(gpbo_ctx* c, const double* cov, int G, int n, double eta, double* sqrtw, int* status, int* iters) {
+    if (!c || !cov || !sqrtw || G <= 0 || n <= 0) return fail(GPBO_EINVAL, "sqrtw_host: bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const size_t bytes = (size_t)G * n * n * 8;
+    CUDA_TRY(c->cov_dev.ensure(bytes));
+    CUDA_TRY(c->w_dev.ensure(bytes));
+    CUDA_TRY(cudaMemcpyAsync(c->cov_dev.p, cov, bytes, cudaMemcpyHostToDevice, s));
+    int rc = sqrtw_device(c, s, c->cov_dev.as<double>(), G, n, eta, c->w_dev.as<double>(), status, iters);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(sqrtw, c->w_dev.p, bytes, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return GPBO_OK;
 }
 
 int gpbo_lstsq_moments(gpbo_ctx* c, const double* t, const double* y, int G, int m, const double* theta,

@@ -8,10 +8,10 @@ object stays picklable (``save``/``load`` via joblib, ``gpkernels.py:423-430``).
 Not re-implemented here (out of the hot path): the float32 gpytorch variant
 ``TORCH_GP_RBFW`` (``gpkernels.py:32-297``).
 
-``sqrtW`` note (SURVEY.md §8a scope note): the GPU computes ``state_estimate``, ``ddt_estimate`` and
-``ddt_covariance``; ``sqrtW = (C + eta I)^(-1/2)`` is then formed on the host from the returned
-covariance with the reference's own formula (``gpkernels.py:496-504``).  It is an API-completeness
-shim outside the four north-star subsystems, excluded from all GPU timings ("next" row N1).
+``sqrtW = (C + eta I)^(-1/2)`` (``gpkernels.py:496-504``) is computed on the GPU as well, while the covariance is
+still in HBM, by a coupled Newton-Schulz iteration on the FP64 tensor tiles (``csrc/kernels_sqrtw.cuh``) instead of
+the reference's ``eigh``; it is ill-posed element-wise and is checked through the identity
+``sqrtW (C + eta I) sqrtW = I``.
 """
 
 from __future__ import annotations
@@ -119,14 +119,6 @@ def draw_restart_points(bounds_log, n_restarts):
     return np.array([rng.uniform(b[:, 0], b[:, 1]) for _ in range(int(n_restarts))]).reshape(-1, 3)
 
 
-def host_sqrtW(C, eta):
-    """``gpkernels.py:496-504`` on the host (shim, see module docstring)."""
-    ev, V = np.linalg.eigh(C + (eta * np.eye(C.shape[0])))
-    if np.any(ev <= 0):
-        raise ValueError("inverse covariance not positive definite, increase eta")
-    return V @ np.diag(1 / np.sqrt(ev)) @ V.T
-
-
 class GP_RBFW:
     """Gaussian process regressor with kernel  sigma^2 exp(-(t-t')^2 / (2 ell^2)) + chi delta(t,t').
 
@@ -174,6 +166,8 @@ class GP_RBFW:
         if training_data.ndim > 1:
             raise ValueError("GP training data must be one-dimensional")
         t_training = np.asarray(t_training, dtype=np.float64)
+        if not (np.all(np.isfinite(t_training)) and np.all(np.isfinite(np.asarray(training_data, dtype=np.float64)))):
+            raise ValueError("Input contains NaN or infinity.")      # sklearn validate_data in GaussianProcessRegressor.fit
         starts = np.vstack([np.zeros((1, 3)), draw_restart_points(self.gpr.bounds_log, self.gpr.n_restarts_optimizer)])
         ctx = _lib.default_context()
         res = ctx.fit(t_training[None, :], training_data[None, :], self.gpr.bounds_log, starts,
@@ -272,12 +266,12 @@ class GP_RBFW:
         """state_estimate, ddt_estimate, ddt_covariance, sqrtW at ``t_est`` (gpkernels.py:612-649, 445-504)."""
         t_est = np.asarray(t_est, dtype=np.float64)
         ctx = _lib.default_context()
-        state, ddt, cov, st = ctx.lstsq_moments(self.t_training[None, :], self.y[None, :],
-                                                self.gpr.kernel_.theta[None, :], t_est)
-        self._set_lstsq_result(t_est, state[0], ddt[0], cov[0], int(st[0]), eta)
+        state, ddt, cov, w, st, wst, _ = ctx.lstsq_weights(self.t_training[None, :], self.y[None, :],
+                                                           self.gpr.kernel_.theta[None, :], t_est, eta)
+        self._set_lstsq_result(t_est, state[0], ddt[0], cov[0], int(st[0]), w[0], int(wst[0]))
         return None
 
-    def _set_lstsq_result(self, t_est, state, ddt, cov, status, eta):
+    def _set_lstsq_result(self, t_est, state, ddt, cov, status, sqrtW, w_status):
         self.t_estimation = t_est
         if status != 0 or not np.all(np.isfinite(cov)):
             # scipy.linalg.cho_factor(K_yy, check_finite=True) raises for the same inputs (gpkernels.py:481)
@@ -285,4 +279,6 @@ class GP_RBFW:
         self.state_estimate = state
         self.ddt_estimate = ddt
         self.ddt_covariance = cov
-        self.sqrtW = host_sqrtW(cov, eta)
+        if w_status != 0:                                  # gpkernels.py:500-503
+            raise ValueError("inverse covariance not positive definite, increase eta")
+        self.sqrtW = sqrtW

@@ -8,7 +8,7 @@ and the GPs are independent for prediction, so one process per GPU takes a cycli
   rank performs the per-GP argmin of sklearn ``_gpr.py:336-340``;
 * one all-gather of the per-GP posterior moments ``alpha_, state_estimate, ddt_estimate`` (+ status).
 
-``ddt_covariance`` (m'^2 per GP) stays on the owning rank (``cov[g] is None`` elsewhere).
+``ddt_covariance`` and ``sqrtW`` (m'^2 per GP each) stay on the owning rank (``cov[g] is None`` elsewhere).
 The collectives go through ``torch.distributed`` (NCCL over NVLink on GPUs; gloo in the CPU tests).
 ``engine`` is anything with the ``_lib.Context`` methods ``fit`` / ``lstsq_moments`` / ``predict``.
 """
@@ -73,19 +73,29 @@ def fit_pairs(engine, T, Y, bounds_log, starts, gp_of, group=None, opts=None):
                 nit=full[:, 5].astype(np.int32), status=full[:, 6].astype(np.int32), evals=evals, rounds=rounds)
 
 
-def moments(engine, T, Y, theta_opt, t_est, group=None, want_cov=True):
-    """alpha_, state/ddt estimates and derivative covariance of every GP; GPs ``rank::world`` per rank."""
+def moments(engine, T, Y, theta_opt, t_est, group=None, want_cov=True, eta=None):
+    """alpha_, state/ddt estimates, derivative covariance (and, when ``eta`` is given, sqrtW) of every GP;
+    GPs ``rank::world`` per rank.  ``cov[g]`` / ``sqrtW[g]`` are None on ranks that do not own GP g."""
     dist, rank, world = _dist(group)
     G, m = T.shape
     n = t_est.shape[-1]
     idx = shard_indices(G, rank, world)
     cov = [None] * G
+    sqrtW = [None] * G
+    w_status = np.zeros(G, dtype=np.int32)
     if idx.size:
-        state, ddt, c, st = engine.lstsq_moments(T[idx], Y[idx], theta_opt[idx], t_est if t_est.ndim == 1 else t_est[idx],
-                                                 want_cov=want_cov)
+        pts = t_est if t_est.ndim == 1 else t_est[idx]
+        if eta is not None:
+            state, ddt, c, w, st, wst, _ = engine.lstsq_weights(T[idx], Y[idx], theta_opt[idx], pts, eta)
+        else:
+            state, ddt, c, st = engine.lstsq_moments(T[idx], Y[idx], theta_opt[idx], pts, want_cov=want_cov)
+            w, wst = None, None
         _, _, alpha, fst = engine.predict(T[idx], Y[idx], theta_opt[idx], T[idx][:, :1], want_alpha=True)
         for k, g in enumerate(idx):
             cov[g] = c[k] if c is not None else None
+            if w is not None:
+                sqrtW[g] = w[k]
+                w_status[g] = wst[k]
         packed = np.column_stack([alpha, state, ddt, st, fst])
     else:
         packed = np.zeros((0, m + 2 * n + 2))
@@ -94,4 +104,5 @@ def moments(engine, T, Y, theta_opt, t_est, group=None, want_cov=True):
     else:
         full = _all_gather_rows(dist, group, packed, G, rank, world)
     return dict(alpha=full[:, :m].copy(), state=full[:, m:m + n].copy(), ddt=full[:, m + n:m + 2 * n].copy(),
-                status=full[:, m + 2 * n].astype(np.int32), fit_status=full[:, m + 2 * n + 1].astype(np.int32), cov=cov)
+                status=full[:, m + 2 * n].astype(np.int32), fit_status=full[:, m + 2 * n + 1].astype(np.int32), cov=cov,
+                sqrtW=sqrtW, w_status=w_status)

@@ -99,6 +99,8 @@ def fit_gaussian_processes_multi(time_domain_training, time_domains_sampled, sna
     T = np.ascontiguousarray(np.vstack(Ts))
     Y = np.ascontiguousarray(np.vstack(Ys))
     G = T.shape[0]
+    if not (np.all(np.isfinite(T)) and np.all(np.isfinite(Y))):
+        raise ValueError("Input contains NaN or infinity.")          # sklearn validate_data in GaussianProcessRegressor.fit
 
     # 1. restart points, in the reference's order (all ranks draw the same stream)
     objs = [GP_RBFW(cb, lb, nb, nres) for _ in range(G)]
@@ -122,7 +124,7 @@ def fit_gaussian_processes_multi(time_domain_training, time_domains_sampled, sna
     theta_opt = np.array([o.gpr.kernel_.theta for o in objs])
 
     # 4. posterior moments of every GP in one batched pass
-    mom = sharding.moments(ctx, T, Y, theta_opt, t_est, group=group)
+    mom = sharding.moments(ctx, T, Y, theta_opt, t_est, group=group, eta=gp_regularizer if want_sqrtW else None)
     for g in range(G):
         o = objs[g]
         o._finish_fit(ctx, alpha=mom["alpha"][g], status=int(mom["fit_status"][g]))
@@ -133,8 +135,11 @@ def fit_gaussian_processes_multi(time_domain_training, time_domains_sampled, sna
             o.t_estimation = t_est
             o.state_estimate, o.ddt_estimate = mom["state"][g], mom["ddt"][g]
             continue
-        o._set_lstsq_result(t_est, mom["state"][g], mom["ddt"][g], cov, int(mom["status"][g]),
-                            gp_regularizer) if want_sqrtW else _set_no_sqrtW(o, t_est, mom, g)
+        if want_sqrtW:
+            o._set_lstsq_result(t_est, mom["state"][g], mom["ddt"][g], cov, int(mom["status"][g]), mom["sqrtW"][g],
+                                int(mom["w_status"][g]))
+        else:
+            _set_no_sqrtW(o, t_est, mom, g)
 
     out, k = [], 0
     for Q in Ys:

@@ -111,11 +111,30 @@ int gpbo_lstsq_moments(gpbo_ctx* ctx, const double* t, const double* y, int G, i
                        const double* t_est, long test_stride, int n_est, double* state, double* ddt, double* cov,
                        int* status, void* stream);
 
+/* Weight matrix of the weighted least squares: sqrtW = (C + eta I)^(-1/2), symmetric.
+ * Replaces la.eigh(C + eta I) -> V diag(lambda^-1/2) V^T of _BaseGP._compute_estimates_and_weights
+ * (gpkernels.py:496-504).  Computed with the coupled Newton-Schulz iteration on the FP64 tensor tiles
+ * (csrc/kernels_sqrtw.cuh).  cov, sqrtw: [G][n][n] DEVICE pointers (the lower triangle of cov is read);
+ * status [G] and iters [G] are HOST arrays (may be NULL): status 1 = C + eta I has an eigenvalue <= 0 to working
+ * precision (the condition for the reference's ValueError "inverse covariance not positive definite,
+ * increase eta", gpkernels.py:500-503); iters = Newton-Schulz iterations used. */
+int gpbo_sqrtw(gpbo_ctx* ctx, const double* cov, int G, int n, double eta, double* sqrtw, int* status, int* iters,
+               void* stream);
+/* Same with HOST cov / sqrtw buffers. */
+int gpbo_sqrtw_host(gpbo_ctx* ctx, const double* cov, int G, int n, double eta, double* sqrtw, int* status,
+                    int* iters);
+/* gpbo_lstsq_moments_host followed by gpbo_sqrtw on the covariance while it is still in HBM: everything
+ * GP_RBFW.compute_lstsq_matrices produces (gpkernels.py:612-649, 445-504) in one call.  w_status / w_iters as in
+ * gpbo_sqrtw (HOST arrays, may be NULL). */
+int gpbo_lstsq_weights_host(gpbo_ctx* ctx, const double* t, const double* y, int G, int m, const double* theta,
+                            const double* t_est, long test_stride, int n_est, double eta, double* state, double* ddt,
+                            double* cov, double* sqrtw, int* status, int* w_status, int* w_iters);
+
 /* Per-kernel-class device timing (CUDA events on the launching stream), for bench.py's roofline.
  * Classes: 0 prep 1 chol_diag 2 chol_panel 3 trsv 4 trtri 5 lauum_grad 6 finalize 7 cross_panel
- *          8 schur 9 mean_std 10 assemble.  `ms` and `launches` are arrays of GPBO_NCLASS entries,
+ *          8 schur 9 mean_std 10 assemble 11 sqrtw.  `ms` and `launches` are arrays of GPBO_NCLASS entries,
  * accumulated since the last gpbo_profile_enable(ctx, 1). */
-#define GPBO_NCLASS 11
+#define GPBO_NCLASS 12
 int gpbo_profile_enable(gpbo_ctx* ctx, int on);
 int gpbo_profile_get(gpbo_ctx* ctx, double* ms, long long* launches);
 

@@ -257,3 +257,77 @@ def test_fit_reaches_reference_optimum(ctx, name, tol):
     for gi in range(G):
         assert abs(best[gi] - g["lml_opt"][gi]) <= tol * abs(g["lml_opt"][gi]), (gi, best[gi], g["lml_opt"][gi])
     assert res["evals"] == int(res["nfev"].sum())
+
+
+# ------------------------------------------------------------------ sqrtW = (C + eta I)^(-1/2)
+def _eigh_sqrtw(C, eta):
+    ev, V = np.linalg.eigh(C + eta * np.eye(C.shape[0]))       # gpkernels.py:496-504
+    return V @ np.diag(1 / np.sqrt(ev)) @ V.T, ev
+
+
+@pytest.mark.parametrize("name", REAL_CONFIGS)
+def test_sqrtw_real_configs(ctx, name):
+    """Newton-Schulz sqrtW on the reference's own derivative covariances: defining identity at least as tight as
+    the reference's eigh route, element-wise agreement at the level the ill-conditioning allows."""
+    g = load_golden(name)
+    C = g["ddt_covariance"]
+    eta = float(g["eta"])
+    W, st, it = ctx.sqrtw(C, eta)
+    assert np.all(st == 0) and np.all(it < 80)
+    for k in range(C.shape[0]):
+        n = C.shape[1]
+        A = C[k] + eta * np.eye(n)
+        Wref, ev = _eigh_sqrtw(C[k], eta)
+        assert np.array_equal(W[k], W[k].T)
+        res = np.abs(W[k] @ A @ W[k] - np.eye(n)).max()
+        res_ref = np.abs(Wref @ A @ Wref - np.eye(n)).max()
+        assert res <= max(3 * res_ref, 1e-9), (name, k, res, res_ref)
+        cond = ev[-1] / ev[0]
+        assert rel(W[k], Wref) <= max(1e-12, 1e-15 * cond * 10), (name, k, cond)
+
+
+@pytest.mark.parametrize("n", [1, 80, 129, 300])
+def test_sqrtw_well_conditioned_matches_eigh(ctx, n):
+    rng = np.random.default_rng(n)
+    M = rng.standard_normal((3, n, n))
+    C = np.einsum("gij,gkj->gik", M, M) / n + 0.5 * np.eye(n)
+    W, st, it = ctx.sqrtw(C, 1e-3)
+    assert np.all(st == 0)
+    for k in range(3):
+        Wref, _ = _eigh_sqrtw(C[k], 1e-3)
+        assert rel(W[k], Wref) <= 1e-12
+
+
+def test_sqrtw_not_positive_definite_status_and_error(ctx, monkeypatch):
+    n = 40
+    rng = np.random.default_rng(0)
+    M = rng.standard_normal((n, n))
+    good = M @ M.T / n + np.eye(n)
+    bad = good.copy()
+    bad -= 3.0 * np.outer(M[:, 0], M[:, 0]) / (M[:, 0] @ M[:, 0]) * np.linalg.eigvalsh(good).max()   # one negative eigenvalue
+    W, st, it = ctx.sqrtw(np.stack([good, bad, -np.eye(n)]), 1e-8)
+    assert list(st) == [0, 1, 1]
+    Wref, _ = _eigh_sqrtw(good, 1e-8)
+    assert rel(W[0], Wref) <= 1e-12
+    # the drop-in raises the reference's ValueError (gpkernels.py:500-503)
+    from gpbo_pkg import pkg
+
+    t, y = orc.synthetic_trajectories(1, 60, seed=2)
+    gp = pkg.GP_RBFW((1e-5, 1e5), (1e-5, 1e2), (1e-16, 1e2), 2).fit(t, y[0])
+    with pytest.raises(ValueError, match="increase eta"):
+        gp.compute_lstsq_matrices(np.linspace(0, 1, 50), eta=-1e6)
+
+
+def test_lstsq_weights_one_call_equals_two(ctx):
+    t, y = orc.synthetic_trajectories(3, 200, seed=9)
+    T = np.tile(t, (3, 1))
+    theta = np.log(np.array([[1.5, 0.05, 1e-2], [0.8, 0.1, 3e-3], [2.0, 0.2, 1e-3]]))
+    t_est = np.linspace(0, 1, 260)
+    s1, d1, c1, st1 = ctx.lstsq_moments(T, y, theta, t_est)
+    w1, wst1, _ = ctx.sqrtw(c1, 1e-8)
+    s2, d2, c2, w2, st2, wst2, _ = ctx.lstsq_weights(T, y, theta, t_est, 1e-8)
+    assert np.array_equal(s1, s2) and np.array_equal(d1, d2) and np.array_equal(c1, c2)
+    assert np.array_equal(w1, w2) and np.array_equal(wst1, wst2)
+    for k in range(3):
+        A = c2[k] + 1e-8 * np.eye(260)
+        assert np.abs(w2[k] @ A @ w2[k] - np.eye(260)).max() <= 1e-5
