@@ -66,6 +66,8 @@ struct gpbo_ctx {
     DevBuf X, trow, tsrc, out1, out2, cov_dev;
     // sqrtW (Newton-Schulz)
     DevBuf nsY, nsZ, nsT, nsTT, nsYn, nsZn, nsPart, nsNorm, nsResid, w_dev;
+    // split-K partial tiles (small batches)
+    DevBuf pre;
     // pinned staging for the optimiser rounds
     double* h_theta = nullptr; double* h_lml = nullptr; double* h_grad = nullptr; int* h_gpof = nullptr;
     size_t h_cap = 0;
@@ -160,6 +162,7 @@ int set_kernel_attrs() {
     CUDA_TRY(cudaFuncSetAttribute(chol_panel_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(chol_panel_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(trtri_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(splitk_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(lauum_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(ns_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
@@ -167,6 +170,34 @@ int set_kernel_attrs() {
     GPBO_SYM_ATTR(0) GPBO_SYM_ATTR(1) GPBO_SYM_ATTR(2) GPBO_SYM_ATTR(3) GPBO_SYM_ATTR(4) GPBO_SYM_ATTR(5) GPBO_SYM_ATTR(6)
 #undef GPBO_SYM_ATTR
     g_attr_done = true;
+    return GPBO_OK;
+}
+
+// Split-K policy: with fewer than ~one CTA per SM in a launch whose tiles run a k-loop of nk_max slices, the loop
+// is cut into up to 16 chunks of >= 4 slices computed by separate CTAs (splitk_partial_kernel) first.
+// Returns a PreAcc with buf == nullptr when the fused kernels should run their own loop.
+int g_sm_count = 0;
+int plan_split(gpbo_ctx* c, cudaStream_t s, const MatArgs& a, int mode, int idx, int nb, int ntile, int nk_max,
+               const double* X, long x_stride, PreAcc* out) {
+    out->buf = nullptr; out->nsplit = 1; out->chunk = nk_max;
+    if (g_sm_count == 0) {
+        cudaDeviceProp prop;
+        CUDA_TRY(cudaGetDeviceProperties(&prop, c->device));
+        g_sm_count = prop.multiProcessorCount;
+    }
+    const long units = (long)nb * ntile;
+    if (units <= 0 || nk_max < 16) return GPBO_OK;
+    int nsplit = (int)std::min<long>(16, g_sm_count / units);
+    nsplit = std::min(nsplit, nk_max / 4);
+    if (nsplit < 2) return GPBO_OK;
+    const int chunk = (nk_max + nsplit - 1) / nsplit;
+    nsplit = (nk_max + chunk - 1) / chunk;
+    CUDA_TRY(c->pre.ensure((size_t)units * nsplit * 64 * NTHR * 8));
+    launch(c, mode == 1 ? C_TRTRI : (mode == 2 ? C_CROSS : C_PANEL), s, [&] {
+        splitk_partial_kernel<<<(unsigned)(units * nsplit), NTHR, MAIN_SMEM, s>>>(a, mode, idx, ntile, nsplit, chunk,
+                                                                                 c->pre.as<double>(), X, x_stride);
+    });
+    out->buf = c->pre.as<double>(); out->nsplit = nsplit; out->chunk = chunk;
     return GPBO_OK;
 }
 
@@ -179,20 +210,23 @@ int factor_wave(gpbo_ctx* c, cudaStream_t s, const MatArgs& a, const double* t_d
     });
     CrossArgs none{nullptr, 0, 0, 0};
     for (int j = 0; j < a.T; ++j) {
+        PreAcc pre;
+        int rc = plan_split(c, s, a, 0, j, nb, a.T - j, j * (TB / BK), nullptr, 0, &pre);
+        if (rc) return rc;
         launch(c, C_DIAG, s, [&] {
-            if (order == 0) chol_diag_kernel<0><<<nb, NTHR, MAIN_SMEM, s>>>(a, j);
-            else chol_diag_kernel<1><<<nb, NTHR, MAIN_SMEM, s>>>(a, j);
+            if (order == 0) chol_diag_kernel<0><<<nb, NTHR, MAIN_SMEM, s>>>(a, j, pre);
+            else chol_diag_kernel<1><<<nb, NTHR, MAIN_SMEM, s>>>(a, j, pre);
         });
         if (j < a.T - 1) {
             const int grid = nb * (a.T - 1 - j);
             launch(c, C_PANEL, s, [&] {
-                if (order == 0) chol_panel_kernel<0, false><<<grid, NTHR, TILE_SMEM, s>>>(a, j, nullptr, 0, 0, none);
-                else chol_panel_kernel<1, false><<<grid, NTHR, TILE_SMEM, s>>>(a, j, nullptr, 0, 0, none);
+                if (order == 0) chol_panel_kernel<0, false><<<grid, NTHR, TILE_SMEM, s>>>(a, j, nullptr, 0, 0, none, pre);
+                else chol_panel_kernel<1, false><<<grid, NTHR, TILE_SMEM, s>>>(a, j, nullptr, 0, 0, none, pre);
             });
         }
     }
-    launch(c, C_TRSV, s, [&] { trsv_fwd_kernel<<<nb, NTHR, 0, s>>>(a, ypad, c->z.as<double>()); });
-    launch(c, C_TRSV, s, [&] { trsv_bwd_kernel<<<nb, NTHR, 0, s>>>(a, c->z.as<double>(), c->alpha.as<double>()); });
+    launch(c, C_TRSV, s, [&] { trsv_fwd_kernel<<<nb, TRSV_THR, 0, s>>>(a, ypad, c->z.as<double>()); });
+    launch(c, C_TRSV, s, [&] { trsv_bwd_kernel<<<nb, TRSV_THR, 0, s>>>(a, c->z.as<double>(), c->alpha.as<double>()); });
     CUDA_TRY(cudaGetLastError());
     return GPBO_OK;
 }
@@ -205,8 +239,12 @@ int eval_wave(gpbo_ctx* c, cudaStream_t s, const double* t_dev, const double* yp
     if (rc) return rc;
     const int ntiles = a.T * (a.T + 1) / 2;
     if (with_grad) {
-        for (int i = 1; i < a.T; ++i)
-            launch(c, C_TRTRI, s, [&] { trtri_row_kernel<<<nb * i, NTHR, TILE_SMEM, s>>>(a, i); });
+        for (int i = 1; i < a.T; ++i) {
+            PreAcc pre;
+            rc = plan_split(c, s, a, 1, i, nb, i, i * (TB / BK), nullptr, 0, &pre);
+            if (rc) return rc;
+            launch(c, C_TRTRI, s, [&] { trtri_row_kernel<<<nb * i, NTHR, TILE_SMEM, s>>>(a, i, pre); });
+        }
         launch(c, C_LAUUM, s, [&] {
             lauum_grad_kernel<<<nb * ntiles, NTHR, MAIN_SMEM, s>>>(a, c->alpha.as<double>(), c->part.as<double>(), ntiles);
         });
@@ -371,7 +409,8 @@ int gpbo_destroy(gpbo_ctx* c) {
     DevBuf* bufs[] = {&c->A, &c->D, &c->DT, &c->ts, &c->z, &c->alpha, &c->pp, &c->logdet, &c->part, &c->status,
                       &c->t_dev, &c->y_dev, &c->ypad, &c->theta_dev, &c->gpof_dev, &c->lml_dev, &c->grad_dev, &c->st_dev,
                       &c->X, &c->trow, &c->tsrc, &c->out1, &c->out2, &c->cov_dev,
-                      &c->nsY, &c->nsZ, &c->nsT, &c->nsTT, &c->nsYn, &c->nsZn, &c->nsPart, &c->nsNorm, &c->nsResid, &c->w_dev};
+                      &c->nsY, &c->nsZ, &c->nsT, &c->nsTT, &c->nsYn, &c->nsZn, &c->nsPart, &c->nsNorm, &c->nsResid, &c->w_dev,
+                      &c->pre};
     for (DevBuf* b : bufs) b->release();
     for (auto& r : c->recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     if (c->h_theta) cudaFreeHost(c->h_theta);
@@ -667,10 +706,14 @@ static int moments_device(gpbo_ctx* c, cudaStream_t s, int mode, const double* t
             CrossArgs crx = cr;
             crx.kind = mode == 0 ? 0 : 2;
             const long xs = (long)n_pad * m_pad;
-            for (int j = 0; j < a.T; ++j)
+            for (int j = 0; j < a.T; ++j) {
+                PreAcc pre;
+                rc = plan_split(c, s, a, 2, j, nb, xT, j * (TB / BK), c->X.as<double>(), xs, &pre);
+                if (rc) return rc;
                 launch(c, C_CROSS, s, [&] {
-                    chol_panel_kernel<0, true><<<nb * xT, NTHR, TILE_SMEM, s>>>(a, j, c->X.as<double>(), xs, xT, crx);
+                    chol_panel_kernel<0, true><<<nb * xT, NTHR, TILE_SMEM, s>>>(a, j, c->X.as<double>(), xs, xT, crx, pre);
                 });
+            }
             if (mode == 0) {
                 launch(c, C_MEAN, s, [&] {
                     std_kernel<<<mgrid, NTHR, 0, s>>>(a, c->X.as<double>(), xs, n, out2 + (size_t)w0 * n, n);

@@ -287,10 +287,86 @@ __device__ __forceinline__ bool potf2_trtri_smem(double* P, double* scratch, dou
     return bad;
 }
 
+// ---- split-K pre-accumulation for small batches --------------------------------------------
+// With few pairs in flight the left-looking k-loops (up to T-1 blocks long) leave most SMs idle and put
+// the whole loop on the critical path of every block column / row.  splitk_partial_kernel then computes the
+// tile products in `nsplit` k-chunks on separate CTAs into a scratch buffer (accumulator layout, fixed order ->
+// deterministic), and the consumer kernels (chol_diag / chol_panel / trtri_row) start from the summed tile
+// instead of running their own loop.
+struct PreAcc {
+    const double* buf;   // [unit][nsplit][64][256] partial accumulators; nullptr: the kernel runs its own k-loop
+    int nsplit;          // chunks per tile
+    int chunk;           // k-slices per chunk
+};
+
+__device__ __forceinline__ void preacc_load(Acc& acc, const PreAcc& pre, long unit, int nk, int tid) {
+    const int nsp = min(pre.nsplit, (nk + pre.chunk - 1) / pre.chunk);
+    for (int sidx = 0; sidx < nsp; ++sidx) {
+        const double* b = pre.buf + ((unit * pre.nsplit + sidx) * 64) * NTHR + tid;
+#pragma unroll
+        for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) acc.v[mi][ni][e] += b[((mi * 4 + ni) * 2 + e) * NTHR];
+    }
+}
+
+// mode 0: Cholesky column idx=j : tile t of pair p is block row j + t (t = 0: diagonal tile), k-slices [0, 8 j)
+// mode 1: trtri row idx=i       : tile t is column block t < i,                             k-slices [0, 8 (i - t))
+// mode 2: prediction TRSM col j : tile t is row block t of X (rows = prediction points),     k-slices [0, 8 j)
+// blockIdx.x = ((p * ntile) + t) * nsplit + chunk index.
+__global__ void __launch_bounds__(NTHR, 1)
+splitk_partial_kernel(MatArgs a, int mode, int idx, int ntile, int nsplit, int chunk, double* __restrict__ buf,
+                      const double* __restrict__ X, long x_stride) {
+    extern __shared__ __align__(16) double smem[];
+    const ThreadCoord tc;
+    const int unit = blockIdx.x / nsplit, sp = blockIdx.x % nsplit;
+    const int p = unit / ntile, t = unit % ntile;
+    const int nk = (mode == 1 ? idx - t : idx) * (TB / BK);
+    const int k0 = sp * chunk, k1 = min(nk, k0 + chunk);
+    if (k0 >= k1) return;
+    const double* Ap = a.A + (long)p * a.mat_stride;
+    __shared__ uint64_t bars[2 * NSTAGE];
+    Ring ring;
+    ring_init(ring, bars);
+    Acc acc;
+    acc_zero(acc);
+    if (mode == 1) {
+        const int i = idx, j = t;
+        const double* Lrow = Ap + (long)i * TB * a.lda;
+        const double* Urow = Ap + (long)j * TB * a.lda;
+        const double* DTj = a.DT + ((long)p * a.T + j) * (TB * TB);
+        gemm_nt_loop<false>(
+            acc,
+            [&](int kk) {
+                const int kt = kk + k0;
+                const double* ap = Lrow + j * TB + kt * BK;
+                return kt < TB / BK ? SliceSrc{ap, a.lda, DTj + kt * BK, TB}
+                                    : SliceSrc{ap, a.lda, Urow + j * TB + kt * BK, a.lda};
+            },
+            k1 - k0, smem, ring, tc);
+    } else {
+        const double* arows = (mode == 2 ? X + (long)p * x_stride + (long)t * TB * a.lda
+                                         : Ap + (long)(idx + t) * TB * a.lda);
+        const double* brows = Ap + (long)idx * TB * a.lda;
+        gemm_nt_loop<false>(
+            acc, [&](int kk) { return SliceSrc{arows + (kk + k0) * BK, a.lda, brows + (kk + k0) * BK, a.lda}; },
+            k1 - k0, smem, ring, tc);
+    }
+    double* b = buf + ((long)blockIdx.x * 64) * NTHR + tc.tid;
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) b[((mi * 4 + ni) * 2 + e) * NTHR] = acc.v[mi][ni][e];
+}
+
 // ---- Cholesky, diagonal tile of block column j ---------------------------------------------
 // S_jj = K_jj - sum_{k<j} L_jk L_jk^T (DMMA);  L_jj = chol(S_jj);  D_j = inv(L_jj).
 template <int ORDER>
-__global__ void __launch_bounds__(NTHR, 1) chol_diag_kernel(MatArgs a, int j) {
+__global__ void __launch_bounds__(NTHR, 1) chol_diag_kernel(MatArgs a, int j, PreAcc pre) {
     extern __shared__ __align__(16) double smem[];
     const ThreadCoord tc;
     const int p = blockIdx.x;
@@ -301,8 +377,11 @@ __global__ void __launch_bounds__(NTHR, 1) chol_diag_kernel(MatArgs a, int j) {
     ring_init(ring, bars);
     Acc acc;
     acc_zero(acc);
-    gemm_nt_loop<true>(acc, [&](int kt) { return SliceSrc{rows + kt * BK, a.lda, nullptr, 0}; }, j * (TB / BK), smem,
-                       ring, tc);
+    if (pre.buf)
+        preacc_load(acc, pre, (long)p * (a.T - j), j * (TB / BK), tc.tid);
+    else
+        gemm_nt_loop<true>(acc, [&](int kt) { return SliceSrc{rows + kt * BK, a.lda, nullptr, 0}; }, j * (TB / BK),
+                           smem, ring, tc);
     __syncthreads();   // every warp is done with the ring: its memory becomes P
 
     double* P = smem;
@@ -375,7 +454,7 @@ __device__ __forceinline__ double cross_element(int kind, const PairParams& q, i
 //                 of the Cholesky of the joint covariance.
 template <int ORDER, bool CROSS>
 __global__ void __launch_bounds__(NTHR, 1)
-chol_panel_kernel(MatArgs a, int j, double* X, long x_stride, int xT, CrossArgs cr) {
+chol_panel_kernel(MatArgs a, int j, double* X, long x_stride, int xT, CrossArgs cr, PreAcc pre) {
     extern __shared__ __align__(16) double smem[];
     const ThreadCoord tc;
     int p, i;
@@ -390,8 +469,11 @@ chol_panel_kernel(MatArgs a, int j, double* X, long x_stride, int xT, CrossArgs 
     ring_init(ring, bars);
     Acc acc;
     acc_zero(acc);
-    gemm_nt_loop<false>(acc, [&](int kt) { return SliceSrc{arows + kt * BK, a.lda, brows + kt * BK, a.lda}; },
-                        j * (TB / BK), smem, ring, tc);
+    if (pre.buf)
+        preacc_load(acc, pre, CROSS ? (long)p * xT + i : (long)p * (a.T - j) + (i - j), j * (TB / BK), tc.tid);
+    else
+        gemm_nt_loop<false>(acc, [&](int kt) { return SliceSrc{arows + kt * BK, a.lda, brows + kt * BK, a.lda}; },
+                            j * (TB / BK), smem, ring, tc);
 
     double* S = smem;
     double* stages = smem + TB * LDS;
@@ -437,8 +519,13 @@ chol_panel_kernel(MatArgs a, int j, double* X, long x_stride, int xT, CrossArgs 
 // ---- forward / backward substitution with the block factor ------------------------------
 // The diagonal-block solves use the block inverses D_j = inv(L_jj) (a 128x128 GEMV each) like the panel
 // TRSM does, instead of a 128-step sequential substitution.
+// One CTA of 1024 threads per pair: the GEMV parts are latency bound on a single SM, so they run with 32 warps
+// and four rows per warp in flight.
+constexpr int TRSV_THR = 1024;
+constexpr int TRSV_RPW = TB / (TRSV_THR / 32);   // rows per warp = 4
+
 // z = L^-1 y (one CTA per pair).  _gpr.py:601 (cho_solve, first half).
-__global__ void __launch_bounds__(NTHR, 1) trsv_fwd_kernel(MatArgs a, const double* __restrict__ ypad, double* z) {
+__global__ void __launch_bounds__(TRSV_THR, 1) trsv_fwd_kernel(MatArgs a, const double* __restrict__ ypad, double* z) {
     __shared__ double xs[TB];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int p = blockIdx.x;
@@ -448,46 +535,55 @@ __global__ void __launch_bounds__(NTHR, 1) trsv_fwd_kernel(MatArgs a, const doub
     for (int jb = 0; jb < a.T; ++jb) {
         const double* rows = Ap + (long)jb * TB * a.lda;
         const int nk = jb * TB;
-        // r = y_j - L[j, 0:nk] z[0:nk]; 16 rows per warp, lanes across k
-        for (int rr = 0; rr < 16; ++rr) {
-            const int r = warp * 16 + rr;
-            const double* Lr = rows + (long)r * a.lda;
-            double s = 0.0;
+        // r = y_j - L[j, 0:nk] z[0:nk]; TRSV_RPW rows per warp at once (z loaded once for them), lanes across k
+        {
+            const int r0 = warp * TRSV_RPW;
+            double sacc[TRSV_RPW];
+#pragma unroll
+            for (int q = 0; q < TRSV_RPW; ++q) sacc[q] = 0.0;
+#pragma unroll 2
             for (int k = 2 * lane; k < nk; k += 64) {
-                const double2 l = *reinterpret_cast<const double2*>(Lr + k);
                 const double2 zz = *reinterpret_cast<const double2*>(zp + k);
-                s += l.x * zz.x + l.y * zz.y;
+#pragma unroll
+                for (int q = 0; q < TRSV_RPW; ++q) {
+                    const double2 l = *reinterpret_cast<const double2*>(rows + (long)(r0 + q) * a.lda + k);
+                    sacc[q] += l.x * zz.x + l.y * zz.y;
+                }
             }
-            s = warp_sum(s);
-            if (lane == 0) xs[r] = yp[jb * TB + r] - s;
+#pragma unroll
+            for (int q = 0; q < TRSV_RPW; ++q) {
+                const double sv = warp_sum(sacc[q]);
+                if (lane == 0) xs[r0 + q] = yp[jb * TB + r0 + q] - sv;
+            }
         }
         __syncthreads();
         // z_j = D_j r  (D_j lower triangular)
         const double* Dj = a.D + ((long)p * a.T + jb) * (TB * TB);
-        for (int rr = 0; rr < 16; ++rr) {
-            const int r = warp * 16 + rr;
-            double s = 0.0;
 #pragma unroll
-            for (int q = 0; q < TB / 32; ++q) {
-                const int c = lane + 32 * q;
-                if (c <= r) s = fma(Dj[r * TB + c], xs[c], s);
+        for (int q = 0; q < TRSV_RPW; ++q) {
+            const int r = warp * TRSV_RPW + q;
+            double sv = 0.0;
+#pragma unroll
+            for (int u = 0; u < TB / 32; ++u) {
+                const int c = lane + 32 * u;
+                if (c <= r) sv = fma(Dj[r * TB + c], xs[c], sv);
             }
-            s = warp_sum(s);
-            if (lane == 0) zp[jb * TB + r] = s;
+            sv = warp_sum(sv);
+            if (lane == 0) zp[jb * TB + r] = sv;
         }
         __syncthreads();
     }
 }
 
 // alpha = L^-T z (one CTA per pair).  _gpr.py:601 (cho_solve, second half).
-__global__ void __launch_bounds__(NTHR, 1) trsv_bwd_kernel(MatArgs a, const double* __restrict__ z, double* alpha) {
+__global__ void __launch_bounds__(TRSV_THR, 1) trsv_bwd_kernel(MatArgs a, const double* __restrict__ z, double* alpha) {
     __shared__ double xs[TB], ws[TB];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int p = blockIdx.x;
     const double* Ap = a.A + (long)p * a.mat_stride;
     const double* zp = z + (long)p * a.lda;
     double* wp = alpha + (long)p * a.lda;
-    for (int k = tid; k < a.lda; k += NTHR) wp[k] = zp[k];
+    for (int k = tid; k < a.lda; k += TRSV_THR) wp[k] = zp[k];
     __syncthreads();
     for (int jb = a.T - 1; jb >= 0; --jb) {
         const double* rows = Ap + (long)jb * TB * a.lda;
@@ -495,25 +591,26 @@ __global__ void __launch_bounds__(NTHR, 1) trsv_bwd_kernel(MatArgs a, const doub
         __syncthreads();
         // alpha_j = inv(L_jj)^T w_j = DT_j w_j  (DT_j upper triangular, rows contiguous)
         const double* DTj = a.DT + ((long)p * a.T + jb) * (TB * TB);
-        for (int rr = 0; rr < 16; ++rr) {
-            const int r = warp * 16 + rr;
-            double s = 0.0;
 #pragma unroll
-            for (int q = 0; q < TB / 32; ++q) {
-                const int c = lane + 32 * q;
-                if (c >= r) s = fma(DTj[r * TB + c], ws[c], s);
+        for (int q = 0; q < TRSV_RPW; ++q) {
+            const int r = warp * TRSV_RPW + q;
+            double sv = 0.0;
+#pragma unroll
+            for (int u = 0; u < TB / 32; ++u) {
+                const int c = lane + 32 * u;
+                if (c >= r) sv = fma(DTj[r * TB + c], ws[c], sv);
             }
-            s = warp_sum(s);
-            if (lane == 0) { xs[r] = s; wp[jb * TB + r] = s; }
+            sv = warp_sum(sv);
+            if (lane == 0) { xs[r] = sv; wp[jb * TB + r] = sv; }
         }
         __syncthreads();
-        // w[0:nk] -= L[j, 0:nk]^T alpha_j ; threads across k (coalesced rows)
+        // w[0:nk] -= L[j, 0:nk]^T alpha_j ; threads across k (coalesced rows), 16 rows in flight per thread
         const int nk = jb * TB;
-        for (int k = tid; k < nk; k += NTHR) {
-            double s = 0.0;
-#pragma unroll 8
-            for (int r = 0; r < TB; ++r) s += rows[(long)r * a.lda + k] * xs[r];
-            wp[k] -= s;
+        for (int k = tid; k < nk; k += TRSV_THR) {
+            double sv = 0.0;
+#pragma unroll 16
+            for (int r = 0; r < TB; ++r) sv += rows[(long)r * a.lda + k] * xs[r];
+            wp[k] -= sv;
         }
         __syncthreads();
     }
@@ -521,7 +618,7 @@ __global__ void __launch_bounds__(NTHR, 1) trsv_bwd_kernel(MatArgs a, const doub
 
 // ---- triangular inverse, block row i:  W_ij = -inv(L_ii) sum_{k=j}^{i-1} L_ik W_kj -----------
 // stored transposed: U[j-block rows][i-block cols] = W_ij^T (upper triangle of the pair's buffer).
-__global__ void __launch_bounds__(NTHR, 1) trtri_row_kernel(MatArgs a, int i) {
+__global__ void __launch_bounds__(NTHR, 1) trtri_row_kernel(MatArgs a, int i, PreAcc pre) {
     extern __shared__ __align__(16) double smem[];
     const ThreadCoord tc;
     const int p = blockIdx.x / i, j = blockIdx.x % i;
@@ -535,13 +632,17 @@ __global__ void __launch_bounds__(NTHR, 1) trtri_row_kernel(MatArgs a, int i) {
     Acc acc;
     acc_zero(acc);
     // k-block j: B[n][k] = W_jj[k][n] = DT_j[n][k];  k-blocks j+1 .. i-1: B[n][k] = U[j*128+n][k]
-    gemm_nt_loop<false>(
-        acc,
-        [&](int kt) {
-            const double* ap = Lrow + j * TB + kt * BK;
-            return kt < TB / BK ? SliceSrc{ap, a.lda, DTj + kt * BK, TB} : SliceSrc{ap, a.lda, Urow + j * TB + kt * BK, a.lda};
-        },
-        (i - j) * (TB / BK), smem, ring, tc);
+    if (pre.buf)
+        preacc_load(acc, pre, (long)p * i + j, (i - j) * (TB / BK), tc.tid);
+    else
+        gemm_nt_loop<false>(
+            acc,
+            [&](int kt) {
+                const double* ap = Lrow + j * TB + kt * BK;
+                return kt < TB / BK ? SliceSrc{ap, a.lda, DTj + kt * BK, TB}
+                                    : SliceSrc{ap, a.lda, Urow + j * TB + kt * BK, a.lda};
+            },
+            (i - j) * (TB / BK), smem, ring, tc);
     double* G = smem;
     double* stages = smem + TB * LDS;
     __syncthreads();   // ring memory is re-used for G
