@@ -98,23 +98,23 @@ __global__ void prep_pairs_kernel(const double* __restrict__ theta, const int* _
 // Returns (to every thread) whether a non-positive pivot was met; *logsum gets sum_i log L_ii.
 //
 // Blocked right-looking algorithm with 32-wide panels:
-//   per panel  (1) chol32_block: the 32x32 diagonal block is factored (32 rank-1 steps, one barrier each) and
-//                  inverted (8 lanes per column) by all threads;
-//              (2) all warps: panel X = A * inv(L_kk)^T;   (3) all warps: trailing A22 -= X X^T (register tiles);
-//   then the off-diagonal blocks of inv(L) by block rows: W_ij = -W_ii * sum_k L_ik W_kj.
-// `scratch` needs PB*(PB+1) doubles during the factorisation and PB*(3*PB+1) during the inversion (re-used).
+//   per panel  (1) chol32_block: the 32x32 diagonal block is factored by all threads (32 rank-1 steps, one
+//                  barrier each);
+//              (2) panel X L_kk^T = A by forward substitution, one thread per row with the row in registers;
+//              (3) all warps: trailing A22 -= X X^T (register tiles);
+//   then the four 32x32 diagonal blocks are inverted concurrently (2 lanes per column), and the off-diagonal
+//   blocks of inv(L) follow by block rows: W_ij = -W_ii * sum_k L_ik W_kj.
+// `scratch` needs PB doubles during the factorisation and PB*(3*PB+1) during the inversion (re-used).
 constexpr int PB = 32;            // panel width
-constexpr int LDW = PB + 1;       // stride of the 32x32 inverse in scratch
 constexpr int LDG = 3 * PB + 1;   // stride of the G scratch of the inversion
-constexpr int POTF_SCRATCH = PB * LDG;   // >= PB*LDW + PB
+constexpr int POTF_SCRATCH = PB * LDG;
 
-// All 256 threads: Cholesky of the 32x32 block at P[o..o+32)^2 (lower part, in place), its inverse W
-// (lower triangular) to Wd (stride LDW, zeros above the diagonal) and transposed into the strict upper part
-// of P, dinv[o+i] = 1 / L_ii.  `rsv` = PB doubles of scratch.  Returns (uniformly) whether a pivot was <= 0.
+// All 256 threads: Cholesky of the 32x32 block at P[o..o+32)^2 (lower part, in place); dinv[o+i] = 1 / L_ii.
+// `rsv` = PB doubles of scratch.  Returns (uniformly) whether a pivot was <= 0.
 //
 // Right-looking with unscaled columns (the column scaling by 1/sqrt(d_j) is applied once at the end), so a
-// step is: broadcast pivot -> rsqrt -> rank-1 update of <= 496 entries by 256 threads -> one barrier.
-__device__ __forceinline__ bool chol32_block(double* P, int o, double* Wd, double* dinv, double* rsv) {
+// step is: broadcast pivot -> reciprocal -> rank-1 update of <= 496 entries by 256 threads -> one barrier.
+__device__ __forceinline__ bool chol32_block(double* P, int o, double* dinv, double* rsv) {
     const int tid = threadIdx.x;
     const int r = tid >> 3, c8 = tid & 7;                 // row of the block, column class
     double* Pr = P + (o + r) * LDP + o;
@@ -122,10 +122,10 @@ __device__ __forceinline__ bool chol32_block(double* P, int o, double* Wd, doubl
     for (int j = 0; j < PB - 1; ++j) {
         double d = P[(o + j) * LDP + o + j];
         if (!(d > 0.0)) { bad = true; d = 1.0; }
-        const double rs = rsqrt(d);
-        if (tid == 0) rsv[j] = rs;
+        const double inv_d = __drcp_rn(d);                 // the only long-latency op on the step's critical path
+        if (tid == 0) rsv[j] = d;
         if (r > j) {
-            const double w = Pr[j] * (rs * rs);
+            const double w = Pr[j] * inv_d;
 #pragma unroll
             for (int q = 0; q < PB / 8; ++q) {
                 const int c = c8 + 8 * q;
@@ -137,8 +137,10 @@ __device__ __forceinline__ bool chol32_block(double* P, int o, double* Wd, doubl
     {
         double d = P[(o + PB - 1) * LDP + o + PB - 1];
         if (!(d > 0.0)) { bad = true; d = 1.0; }
-        if (tid == 0) rsv[PB - 1] = rsqrt(d);
+        if (tid == 0) rsv[PB - 1] = d;
     }
+    __syncthreads();
+    if (tid < PB) rsv[tid] = rsqrt(rsv[tid]);              // all 32 square roots at once
     __syncthreads();
     // scale: L_rc = a_rc * rs_c (c < r), L_cc = d_c * rs_c
 #pragma unroll
@@ -151,73 +153,41 @@ __device__ __forceinline__ bool chol32_block(double* P, int o, double* Wd, doubl
     }
     if (tid < PB) dinv[o + tid] = rsv[tid];               // 1 / L_ii = rs_i  (L_ii = d_i rs_i = sqrt(d_i))
     __syncthreads();
-    // inverse: 8 lanes per column jc (tid>>3), forward substitution over rows; the k-sum is split over the 8 lanes
-    {
-        const int jc = tid >> 3, h = tid & 7;
-        const unsigned FULL = 0xffffffffu;
-        for (int rr = 0; rr < PB; ++rr) {
-            // warp-uniform loop; groups with rr <= jc only publish the known entries
-            double sacc = 0.0;
-            if (rr > jc) {
-                const double* Lr = P + (o + rr) * LDP + o;
-                for (int k = jc + h; k < rr; k += 8) sacc = fma(Lr[k], Wd[k * LDW + jc], sacc);
-            }
-            sacc += __shfl_xor_sync(FULL, sacc, 1);
-            sacc += __shfl_xor_sync(FULL, sacc, 2);
-            sacc += __shfl_xor_sync(FULL, sacc, 4);
-            if (h == 0) {
-                const double wv = (rr == jc) ? rsv[rr] : ((rr > jc) ? -sacc * rsv[rr] : 0.0);
-                Wd[rr * LDW + jc] = wv;
-                if (rr > jc) P[(o + jc) * LDP + o + rr] = wv;
-            }
-            __syncwarp();
-        }
-    }
-    __syncthreads();
     return bad;
 }
 
 __device__ __forceinline__ bool potf2_trtri_smem(double* P, double* scratch, double* dinv, double* logsum_out) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     bool bad = false;
-    double* Wd = scratch;
-    double* rsv = scratch + PB * LDW;
+    double* rsv = scratch;
     __syncthreads();   // P was just filled by all threads
     for (int kb = 0; kb < TB / PB; ++kb) {
         const int o = kb * PB;
-        bad |= chol32_block(P, o, Wd, dinv, rsv);
+        bad |= chol32_block(P, o, dinv, rsv);
         const int R0 = o + PB, n = TB - R0;
         if (n <= 0) break;
-        // (2) panel: X[r][c] = sum_{k<=c} A[r][o+k] W[c][k]
-        {
-            const int rr = tid >> 3, cq = tid & 7;
-            double x[3][4];
+        // (2) panel by forward substitution, one thread per row:  X L_kk^T = A  (row in registers, L_kk broadcast)
+        if (tid < n) {
+            double* Ar = P + (R0 + tid) * LDP + o;
+            const double* Lk = P + o * LDP + o;
+            double x[PB];
 #pragma unroll
-            for (int t = 0; t < 3; ++t) {
+            for (int c = 0; c < PB; ++c) x[c] = Ar[c];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) x[t][q] = 0.0;
-                const int r = R0 + rr + 32 * t;
-                if (r < TB) {
-                    const double* Ar = P + r * LDP + o;
-#pragma unroll 16
-                    for (int k = 0; k < PB; ++k) {
-                        const double av = Ar[k];
+            for (int c = 0; c < PB; ++c) {
+                double s0 = x[c], s1 = 0.0;
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) x[t][q] = fma(av, Wd[(cq + 8 * q) * LDW + k], x[t][q]);
-                    }
+                for (int k = 0; k + 1 < c; k += 2) {
+                    s0 = fma(-x[k], Lk[c * LDP + k], s0);
+                    s1 = fma(-x[k + 1], Lk[c * LDP + k + 1], s1);
                 }
+                if (c & 1) s0 = fma(-x[c - 1], Lk[c * LDP + c - 1], s0);
+                x[c] = (s0 + s1) * dinv[o + c];
             }
-            __syncthreads();
 #pragma unroll
-            for (int t = 0; t < 3; ++t) {
-                const int r = R0 + rr + 32 * t;
-                if (r < TB) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) P[r * LDP + o + cq + 8 * q] = x[t][q];
-                }
-            }
-            __syncthreads();
+            for (int c = 0; c < PB; ++c) Ar[c] = x[c];
         }
+        __syncthreads();
         // (3) trailing update of the lower triangle: A[r][c] -= sum_k X[r][k] X[c][k]
         {
             const int ty = tid >> 4, tx = tid & 15;
@@ -252,6 +222,32 @@ __device__ __forceinline__ bool potf2_trtri_smem(double* P, double* scratch, dou
         }
         __syncthreads();
     }
+    // inverses of the four 32x32 diagonal blocks, all at once: 64 threads per block, 2 lanes per column jc,
+    // forward substitution over the rows; W is written transposed into the strict upper part of P, where the
+    // column under construction is contiguous.
+    {
+        const int o = (tid >> 6) * PB, jc = (tid & 63) >> 1, h = tid & 1;
+        double* Wc = P + (o + jc) * LDP + o;           // Wc[k] = W[k][jc], k > jc
+        const double wjj = dinv[o + jc];
+        for (int rr = 1; rr < PB; ++rr) {
+            double s0 = 0.0, s1 = 0.0;
+            if (rr > jc) {
+                const double* Lr = P + (o + rr) * LDP + o;
+                if (h == 0) s0 = Lr[jc] * wjj;
+                int k = jc + 1 + h;
+                for (; k + 2 < rr; k += 4) {
+                    s0 = fma(Lr[k], Wc[k], s0);
+                    s1 = fma(Lr[k + 2], Wc[k + 2], s1);
+                }
+                if (k < rr) s0 = fma(Lr[k], Wc[k], s0);
+            }
+            double sacc = s0 + s1;
+            sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+            if (h == 0 && rr > jc) Wc[rr] = -sacc * dinv[o + rr];
+            __syncwarp();
+        }
+    }
+    __syncthreads();
     // off-diagonal blocks of W = inv(L), block row bi; W stored transposed in the strict upper part of P
     double* Gs = scratch;
     for (int bi = 1; bi < TB / PB; ++bi) {
@@ -260,20 +256,30 @@ __device__ __forceinline__ bool potf2_trtri_smem(double* P, double* scratch, dou
         const double* Lr = P + r * LDP;
         for (int col = warp; col < ncol; col += NTHR / 32) {
             const double* Wc = P + col * LDP;            // Wc[k] = W[k][col] for k > col
-            double g = Lr[col] * dinv[col];
-            for (int k = col + 1; k < oi; ++k) g = fma(Lr[k], Wc[k], g);
-            Gs[lane * LDG + col] = g;
+            // four independent partial sums: the dot product is a dependent-FMA chain otherwise
+            double g0 = Lr[col] * dinv[col], g1 = 0.0, g2 = 0.0, g3 = 0.0;
+            int k = col + 1;
+            for (; k + 3 < oi; k += 4) {
+                g0 = fma(Lr[k], Wc[k], g0);
+                g1 = fma(Lr[k + 1], Wc[k + 1], g1);
+                g2 = fma(Lr[k + 2], Wc[k + 2], g2);
+                g3 = fma(Lr[k + 3], Wc[k + 3], g3);
+            }
+            for (; k < oi; ++k) g0 = fma(Lr[k], Wc[k], g0);
+            Gs[lane * LDG + col] = (g0 + g1) + (g2 + g3);
         }
         __syncthreads();
         for (int col = warp; col < ncol; col += NTHR / 32) {
-            double acc = dinv[r] * Gs[lane * LDG + col];
-            for (int ap = 0; ap < PB; ++ap) {
+            double a0 = dinv[r] * Gs[lane * LDG + col], a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+            for (int ap = 0; ap < PB; ap += 4) {
                 // W_ii[lane][ap] for ap < lane is stored at P[oi+ap][oi+lane]
-                const double wv = P[(oi + ap) * LDP + r];
-                const double gv = Gs[ap * LDG + col];
-                if (ap < lane) acc = fma(wv, gv, acc);
+                if (ap < lane) a0 = fma(P[(oi + ap) * LDP + r], Gs[ap * LDG + col], a0);
+                if (ap + 1 < lane) a1 = fma(P[(oi + ap + 1) * LDP + r], Gs[(ap + 1) * LDG + col], a1);
+                if (ap + 2 < lane) a2 = fma(P[(oi + ap + 2) * LDP + r], Gs[(ap + 2) * LDG + col], a2);
+                if (ap + 3 < lane) a3 = fma(P[(oi + ap + 3) * LDP + r], Gs[(ap + 3) * LDG + col], a3);
             }
-            P[col * LDP + r] = -acc;
+            P[col * LDP + r] = -((a0 + a1) + (a2 + a3));
         }
         __syncthreads();
     }

@@ -132,6 +132,32 @@ def test_replicated_pairs_are_bitwise_identical(ctx):
     assert np.all(state == state[0]) and np.all(ddt == ddt[0]) and np.all(cov == cov[0])
 
 
+@pytest.mark.parametrize("m,B", [(4096, 3), (16384, 1)])
+def test_full_size_gradient_matches_finite_differences(ctx, m, B):
+    """BASELINE sizes (configs[3]: m = 4096, configs[4]: m = 16384), where the CPU oracle is too slow to run in a
+    test: the analytic gradient (K^-1 trace reductions) must equal central differences of the LML itself --
+    a size-independent consistency property between the Cholesky/solve path and the trtri/lauum path."""
+    t, y = orc.synthetic_trajectories(B, m, seed=17)
+    T = np.tile(t, (B, 1))
+    th0 = np.log(np.array([[1.5, 0.05, 1e-2], [0.6, 0.02, 3e-2], [3.0, 0.1, 5e-3]])[:B])
+    h = 1e-4
+    thetas, gp_of = [th0], [np.arange(B)]
+    for i in range(3):
+        for sgn in (+1, -1):
+            d = th0.copy()
+            d[:, i] += sgn * h
+            thetas.append(d)
+            gp_of.append(np.arange(B))
+    lml, grad, st = ctx.lml_grad(T, y, np.vstack(thetas), np.concatenate(gp_of).astype(np.int32))
+    assert np.all(st == 0) and np.all(np.isfinite(lml)) and np.all(np.isfinite(grad))
+    lml = lml.reshape(7, B)
+    g = grad[:B]
+    for i in range(3):
+        fd = (lml[1 + 2 * i] - lml[2 + 2 * i]) / (2 * h)
+        scale = np.maximum(1.0, np.abs(g).max(1))
+        assert np.all(np.abs(fd - g[:, i]) <= 2e-3 * scale), (m, i, fd, g[:, i])
+
+
 # ------------------------------------------------------------------ assembly
 @pytest.mark.parametrize("n1,n2", [(90, 90), (257, 33), (400, 200)])
 def test_assemble_kinds(ctx, n1, n2):
