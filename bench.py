@@ -251,11 +251,14 @@ def main():
     T_blocks = (m + 127) // 128
     m_pad = T_blocks * 128
     blk = 2.0 * 128 ** 3
+    # structural-zero skipping (tile_engine.cuh): symmetric diagonal tiles issue 136/256 of their 8x8 blocks; a k-block
+    # with a triangular block inverse as row operand issues 36/64, as column operand 40/64 of its DMMAs
+    SYM, TRI_A, TRI_B = 136.0 / 256.0, 36.0 / 64.0, 40.0 / 64.0
     issued_pp = {
-        "chol_diag": blk * sum(j for j in range(T_blocks)),
-        "chol_panel": blk * sum((T_blocks - 1 - j) * (j + 1) for j in range(T_blocks)),
-        "trtri": blk * sum(i - j + 1 for i in range(1, T_blocks) for j in range(i)),
-        "lauum_grad": blk * sum((i + 1) * (T_blocks - i) for i in range(T_blocks)),
+        "chol_diag": blk * SYM * sum(j for j in range(T_blocks)),
+        "chol_panel": blk * sum((T_blocks - 1 - j) * (j + TRI_B) for j in range(T_blocks)),
+        "trtri": blk * sum((i - j - 1) + TRI_B + TRI_A for i in range(1, T_blocks) for j in range(i)),
+        "lauum_grad": blk * sum(i * ((T_blocks - i - 1) + TRI_A) + SYM * (T_blocks - i) for i in range(T_blocks)),
     }
     dom = max(("chol_panel", "trtri", "lauum_grad"), key=lambda k: prof[k][0])
     cap = min(B, ctx.wave_capacity(m))

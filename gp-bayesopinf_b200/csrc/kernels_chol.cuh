@@ -641,7 +641,7 @@ __global__ void __launch_bounds__(NTHR, 1) trtri_row_kernel(MatArgs a, int i, Pr
     if (pre.buf)
         preacc_load(acc, pre, (long)p * i + j, (i - j) * (TB / BK), tc.tid);
     else
-        gemm_nt_loop<false>(
+        gemm_nt_loop<false, SKIP_B_UP>(
             acc,
             [&](int kt) {
                 const double* ap = Lrow + j * TB + kt * BK;
@@ -696,7 +696,7 @@ lauum_grad_kernel(MatArgs a, const double* __restrict__ alpha, double* __restric
     // k-block I comes from the diagonal-block inverse DT_I (row stride 128), k-blocks I+1.. from U (row stride lda)
     const int nk = (a.T - I) * (TB / BK);
     if (I == J) {
-        gemm_nt_loop<true>(
+        gemm_nt_loop<true, SKIP_A_UP>(
             acc,
             [&](int kt) {
                 return kt < TB / BK ? SliceSrc{DTI + kt * BK, TB, nullptr, 0}
@@ -704,7 +704,7 @@ lauum_grad_kernel(MatArgs a, const double* __restrict__ alpha, double* __restric
             },
             nk, smem, ring, tc);
     } else {
-        gemm_nt_loop<false>(
+        gemm_nt_loop<false, SKIP_A_UP>(
             acc,
             [&](int kt) {
                 const double* bp = UJ + I * TB + kt * BK;
@@ -723,11 +723,16 @@ lauum_grad_kernel(MatArgs a, const double* __restrict__ alpha, double* __restric
     for (int ni = 0; ni < 4; ++ni)
 #pragma unroll
         for (int e = 0; e < 2; ++e) { xc[ni][e] = tsp[J * TB + tc.col(ni, e)]; ac[ni][e] = al[J * TB + tc.col(ni, e)]; }
+    // Off-diagonal tiles stand for (I,J) and (J,I): weight 2.  On a diagonal tile only the 8x8 blocks on or below
+    // the diagonal were computed: blocks strictly below count twice, diagonal blocks hold both (r,c) and (c,r).
     double s[3] = {0.0, 0.0, 0.0};
 #pragma unroll
     for (int mi = 0; mi < 8; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni)
+        for (int ni = 0; ni < 4; ++ni) {
+            const int gr = tc.rgroup(mi), gc = tc.cgroup(ni);
+            if (I == J && gc > gr) continue;
+            const double wgt = (I != J || gc < gr) ? 2.0 : 1.0;
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int r = I * TB + tc.row(mi), c = J * TB + tc.col(ni, e);
@@ -740,17 +745,17 @@ lauum_grad_kernel(MatArgs a, const double* __restrict__ alpha, double* __restric
                         const double d = xr[mi] - xc[ni][e];
                         const double d2 = d * d;
                         const double kr = pr.sig2 * gpbo_exp(-0.5 * d2);
-                        s[0] += w * kr;
-                        s[1] += w * (kr * d2);
+                        s[0] += wgt * (w * kr);
+                        s[1] += wgt * (w * (kr * d2));
                     }
                 }
             }
+        }
     double tot[3];
     block_sum<3>(s, smem, tot);
     if (tc.tid == 0) {
-        const double f = (I == J) ? 1.0 : 2.0;
         double* o = part + ((long)p * ntiles + q) * 4;
-        o[0] = f * tot[0]; o[1] = f * tot[1]; o[2] = tot[2]; o[3] = 0.0;
+        o[0] = tot[0]; o[1] = tot[1]; o[2] = tot[2]; o[3] = 0.0;
     }
 }
 

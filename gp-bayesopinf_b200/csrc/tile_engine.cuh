@@ -1,5 +1,13 @@
-// FP64 DMMA tile engine: 128x128 output tile per CTA, 8 warps (2x4), warp tile 64x32,
+// FP64 DMMA tile engine: 128x128 output tile per CTA, 8 warps (2x4), 64x32 accumulator elements per warp,
 // k-slices of 16 staged with cp.async into a 4-deep shared ring (see common.cuh).
+//
+// The 8x8 DMMA blocks of a warp are INTERLEAVED over the tile: warp (wm, wn) owns the 8-row groups
+// GR = 2 mi + wm (mi = 0..7) and the 8-column groups GC = 4 ni + wn (ni = 0..3).  Every warp therefore sees the
+// same share of any triangular / symmetric structure, and -- because the two warps of an SM sub-partition are
+// (0, wn) and (1, wn) -- so does every sub-partition.  That is what makes skipping structurally-zero DMMA blocks
+// pay: diagonal (symmetric) tiles issue only the blocks GC <= GR, products with a triangular block inverse
+// (D / DT) skip the 8-row or 8-column groups that lie entirely in the zero part.  (With contiguous 64x32 warp
+// tiles the skipped work piles up on some sub-partitions and the CTA is no faster.)
 //
 // Stage hand-over uses two mbarriers per stage instead of __syncthreads():
 //   full[s]  (count 256): every thread issues its share of the slice with cp.async and then
@@ -23,9 +31,15 @@ struct ThreadCoord {
         g = lane >> 2; c = lane & 3; wm = warp >> 2; wn = warp & 3;
     }
     // accumulator element (mi, ni, e) -> tile row / col
-    __device__ __forceinline__ int row(int mi) const { return wm * 64 + mi * 8 + g; }
-    __device__ __forceinline__ int col(int ni, int e) const { return wn * 32 + ni * 8 + 2 * c + e; }
+    __device__ __forceinline__ int rgroup(int mi) const { return 2 * mi + wm; }      // 8-row group index 0..15
+    __device__ __forceinline__ int cgroup(int ni) const { return 4 * ni + wn; }      // 8-column group index 0..15
+    __device__ __forceinline__ int row(int mi) const { return rgroup(mi) * 8 + g; }
+    __device__ __forceinline__ int col(int ni, int e) const { return cgroup(ni) * 8 + 2 * c + e; }
 };
+
+// fragment geometry in a staged operand: first row of this lane, rows between consecutive mi / ni
+constexpr int FRAG_A_STEP = 16;     // rows between the 8-row groups of one warp
+constexpr int FRAG_B_STEP = 32;     // rows (= output columns) between the 8-column groups of one warp
 
 // ---- the stage ring ---------------------------------------------------------------------------
 // `count` = slices pushed through the ring so far by this CTA; it is carried across successive loops of
@@ -93,21 +107,92 @@ __device__ __forceinline__ void stage_slice(double* s, const double* __restrict_
     }
 }
 
-// Two of the four k-steps (HALF = 0: ks 0,1; HALF = 1: ks 2,3) of DMMA on one staged pair of slices.
-// sa/sb already point at this thread's first fragment element: s?[(w?*.. + g) * stride + c].
-template <int SA_STRIDE, int SB_STRIDE, int HALF>
+// structural-zero skipping.  A predicated-off DMMA still occupies the tensor pipe (measured, tools/dmma_pred.cu:
+// 16 of 32 DMMAs predicated off or individually branched over -> same time; one branch around the 16 -> half), so
+// skipping is done by dispatching -- switch on the warp or on the slice index -- to bodies that simply do not
+// contain the dead DMMAs.
+constexpr int SKIP_SYM = 1;         // symmetric output tile: only blocks GC <= GR            (switch on the warp)
+constexpr int SKIP_A_UP = 2;        // A[r][k] != 0 only for k >= r  (DT as the row operand)    (switch on kt)
+constexpr int SKIP_A_LO = 4;        // A[r][k] != 0 only for k <= r  (D as the row operand)
+constexpr int SKIP_B_UP = 8;        // B[n][k] != 0 only for k >= n  (DT as the column operand)
+constexpr int SKIP_B_LO = 16;       // B[n][k] != 0 only for k <= n  (D as the column operand)
+
+// Two of the four k-steps (HALF = 0: ks 0,1; HALF = 1: ks 2,3) of DMMA on one staged pair of slices, restricted
+// to the accumulator blocks mi in [MI0, MI1), ni in [NI0, NI1).
+// sa/sb already point at this thread's first fragment element: s?[(w? * 8 + g) * stride + c].
+template <int SA_STRIDE, int SB_STRIDE, int HALF, int MI0 = 0, int MI1 = 8, int NI0 = 0, int NI1 = 4>
 __device__ __forceinline__ void mma_half(Acc& acc, const double* sa, const double* sb) {
 #pragma unroll
     for (int ks = HALF * (BK / 8); ks < (HALF + 1) * (BK / 8); ++ks) {
         double a[8], b[4];
 #pragma unroll
-        for (int mi = 0; mi < 8; ++mi) a[mi] = sa[mi * 8 * SA_STRIDE + ks * 4];
+        for (int mi = MI0; mi < MI1; ++mi) a[mi] = sa[mi * FRAG_A_STEP * SA_STRIDE + ks * 4];
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) b[ni] = sb[ni * 8 * SB_STRIDE + ks * 4];
+        for (int ni = NI0; ni < NI1; ++ni) b[ni] = sb[ni * FRAG_B_STEP * SB_STRIDE + ks * 4];
+#pragma unroll
+        for (int mi = MI0; mi < MI1; ++mi)
+#pragma unroll
+            for (int ni = NI0; ni < NI1; ++ni) dmma884(acc.v[mi][ni], a[mi], b[ni]);
+    }
+}
+
+// Same for a symmetric (diagonal) tile: warp (WM, WN) computes only its blocks with 4 ni + WN <= 2 mi + WM.
+template <int SA_STRIDE, int SB_STRIDE, int HALF, int WM, int WN>
+__device__ __forceinline__ void mma_half_sym(Acc& acc, const double* sa, const double* sb) {
+#pragma unroll
+    for (int ks = HALF * (BK / 8); ks < (HALF + 1) * (BK / 8); ++ks) {
+        double a[8], b[4];
+#pragma unroll
+        for (int mi = 0; mi < 8; ++mi)
+            if (WN <= 2 * mi + WM) a[mi] = sa[mi * FRAG_A_STEP * SA_STRIDE + ks * 4];
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+            if (4 * ni + WN <= 14 + WM) b[ni] = sb[ni * FRAG_B_STEP * SB_STRIDE + ks * 4];
 #pragma unroll
         for (int mi = 0; mi < 8; ++mi)
 #pragma unroll
-            for (int ni = 0; ni < 4; ++ni) dmma884(acc.v[mi][ni], a[mi], b[ni]);
+            for (int ni = 0; ni < 4; ++ni)
+                if (4 * ni + WN <= 2 * mi + WM) dmma884(acc.v[mi][ni], a[mi], b[ni]);
+    }
+}
+
+template <int SA_STRIDE, int SB_STRIDE, int HALF>
+__device__ __forceinline__ void mma_half_sym_dispatch(Acc& acc, const double* sa, const double* sb, int warp) {
+    switch (warp) {   // warp = wm * 4 + wn
+        case 0: mma_half_sym<SA_STRIDE, SB_STRIDE, HALF, 0, 0>(acc, sa, sb); break;
+        case 1: mma_half_sym<SA_STRIDE, SB_STRIDE, HALF, 0, 1>(acc, sa, sb); break;
+        case 2: mma_half_sym<SA_STRIDE, SB_STRIDE, HALF, 0, 2>(acc, sa, sb); break;
+        case 3: mma_half_sym<SA_STRIDE, SB_STRIDE, HALF, 0, 3>(acc, sa, sb); break;
+        case 4: mma_half_sym<SA_STRIDE, SB_STRIDE, HALF, 1, 0>(acc, sa, sb); break;
+        case 5: mma_half_sym<SA_STRIDE, SB_STRIDE, HALF, 1, 1>(acc, sa, sb); break;
+        case 6: mma_half_sym<SA_STRIDE, SB_STRIDE, HALF, 1, 2>(acc, sa, sb); break;
+        default: mma_half_sym<SA_STRIDE, SB_STRIDE, HALF, 1, 3>(acc, sa, sb); break;
+    }
+}
+
+// One slice (kt = 0..7) of a k-block in which an operand is a triangular block inverse: the 8-row (8-column)
+// groups that lie entirely in its zero part are left out.  With the interleaved layout the live set is the
+// same for every warp:  A_UP: mi <= kt;   A_LO: mi >= kt;   B_UP: ni <= (2 kt + 1) / 4;   B_LO: ni >= ceil((2 kt - 3) / 4).
+template <int SA_STRIDE, int SB_STRIDE, int HALF, int KIND, int KT>
+__device__ __forceinline__ void mma_half_tri_case(Acc& acc, const double* sa, const double* sb) {
+    constexpr int MI0 = (KIND == SKIP_A_LO) ? KT : 0;
+    constexpr int MI1 = (KIND == SKIP_A_UP) ? KT + 1 : 8;
+    constexpr int NI0 = (KIND == SKIP_B_LO) ? (2 * KT - 3 > 0 ? (2 * KT - 3 + 3) / 4 : 0) : 0;
+    constexpr int NI1 = (KIND == SKIP_B_UP) ? (2 * KT + 1) / 4 + 1 : 4;
+    mma_half<SA_STRIDE, SB_STRIDE, HALF, MI0, MI1, NI0, NI1>(acc, sa, sb);
+}
+
+template <int SA_STRIDE, int SB_STRIDE, int HALF, int KIND>
+__device__ __forceinline__ void mma_half_tri_dispatch(Acc& acc, const double* sa, const double* sb, int kt) {
+    switch (kt) {
+        case 0: mma_half_tri_case<SA_STRIDE, SB_STRIDE, HALF, KIND, 0>(acc, sa, sb); break;
+        case 1: mma_half_tri_case<SA_STRIDE, SB_STRIDE, HALF, KIND, 1>(acc, sa, sb); break;
+        case 2: mma_half_tri_case<SA_STRIDE, SB_STRIDE, HALF, KIND, 2>(acc, sa, sb); break;
+        case 3: mma_half_tri_case<SA_STRIDE, SB_STRIDE, HALF, KIND, 3>(acc, sa, sb); break;
+        case 4: mma_half_tri_case<SA_STRIDE, SB_STRIDE, HALF, KIND, 4>(acc, sa, sb); break;
+        case 5: mma_half_tri_case<SA_STRIDE, SB_STRIDE, HALF, KIND, 5>(acc, sa, sb); break;
+        case 6: mma_half_tri_case<SA_STRIDE, SB_STRIDE, HALF, KIND, 6>(acc, sa, sb); break;
+        default: mma_half_tri_case<SA_STRIDE, SB_STRIDE, HALF, KIND, 7>(acc, sa, sb); break;
     }
 }
 
@@ -121,15 +206,18 @@ struct SliceSrc {
 };
 
 // acc += A * B^T over nk k-slices; src(kt) -> SliceSrc.  SAME: both operands are the same rows
-// (diagonal tiles) -> staged once (src.b ignored).  On return every warp has finished its DMMAs but other
-// warps may still be reading the ring: callers __syncthreads() before re-using `smem` for something else.
-template <bool SAME, class SRC>
+// (diagonal tiles) -> staged once (src.b ignored) and only the blocks on or below the diagonal are computed
+// (the rest of acc stays zero).  TRI1: one SKIP_* kind that holds for the first k-block (slices 0..7), e.g.
+// SKIP_A_UP when the row operand of that block is a transposed block inverse (ignored on SAME tiles).  On return
+// every warp has finished its
+// DMMAs but other warps may still be reading the ring: callers __syncthreads() before re-using `smem`.
+template <bool SAME, int TRI1 = 0, class SRC>
 __device__ __forceinline__ void gemm_nt_loop(Acc& acc, SRC src, int nk, double* smem, Ring& ring,
                                              const ThreadCoord& tc) {
     double* sA = smem;
     double* sB = smem + NSTAGE * STAGE_DBL;
-    const int oa = (tc.wm * 64 + tc.g) * LDT + tc.c;
-    const int ob = (tc.wn * 32 + tc.g) * LDT + tc.c;
+    const int oa = (tc.wm * 8 + tc.g) * LDT + tc.c;
+    const int ob = (tc.wn * 8 + tc.g) * LDT + tc.c;
     ring_pipeline(
         ring, nk,
         [&](int st, int kt) {
@@ -137,10 +225,16 @@ __device__ __forceinline__ void gemm_nt_loop(Acc& acc, SRC src, int nk, double* 
             stage_slice(sA + st * STAGE_DBL, s.a, s.lda, tc.tid);
             if (!SAME) stage_slice(sB + st * STAGE_DBL, s.b, s.ldb, tc.tid);
         },
-        [&](int st, int, auto half) {
+        [&](int st, int kt, auto half) {
             const double* sa = sA + st * STAGE_DBL + oa;
             const double* sb = (SAME ? sA : sB) + st * STAGE_DBL + ob;
-            mma_half<LDT, LDT, decltype(half)::value>(acc, sa, sb);
+            constexpr int H = decltype(half)::value;
+            if (SAME)
+                mma_half_sym_dispatch<LDT, LDT, H>(acc, sa, sb, tc.warp);
+            else if (TRI1 != 0 && kt < TB / BK)
+                mma_half_tri_dispatch<LDT, LDT, H, TRI1>(acc, sa, sb, kt);
+            else
+                mma_half<LDT, LDT, H>(acc, sa, sb);
         });
 }
 
@@ -158,41 +252,56 @@ __device__ __forceinline__ void acc_to_smem(const Acc& acc, double* S, const Thr
 }
 
 // out += S * Dm^T : S is a shared 128x128 tile [r][k] (stride LDS), complete and visible to the CTA;
-// Dm is a 128x128 global block (row stride 128) whose rows [n][k] are streamed through `stages`.
+// Dm is a LOWER-TRIANGULAR 128x128 global block (a block inverse D, row stride 128) whose rows [n][k] are streamed
+// through `stages`; column groups that lie entirely above the diagonal of Dm are skipped.
 __device__ __forceinline__ void epi_product_SxDt(Acc& out, const double* S, const double* __restrict__ Dm,
                                                  double* stages, Ring& ring, const ThreadCoord& tc) {
-    const double* sa0 = S + (tc.wm * 64 + tc.g) * LDS + tc.c;
-    const int ob = (tc.wn * 32 + tc.g) * LDT + tc.c;
+    const double* sa0 = S + (tc.wm * 8 + tc.g) * LDS + tc.c;
+    const int ob = (tc.wn * 8 + tc.g) * LDT + tc.c;
     ring_pipeline(
         ring, TB / BK, [&](int st, int kt) { stage_slice(stages + st * STAGE_DBL, Dm + kt * BK, TB, tc.tid); },
         [&](int st, int kt, auto half) {
-            mma_half<LDS, LDT, decltype(half)::value>(out, sa0 + kt * BK, stages + st * STAGE_DBL + ob);
+            mma_half_tri_dispatch<LDS, LDT, decltype(half)::value, SKIP_B_LO>(out, sa0 + kt * BK,
+                                                                              stages + st * STAGE_DBL + ob, kt);
         });
 }
 
-// out += Dm * G : Dm is a 128x128 global block [r][k] streamed through `stages`;
-// G is a shared 128x128 tile stored [k][n] (stride LDS), complete and visible to the CTA.
+// out += Dm * G : Dm is a LOWER-TRIANGULAR 128x128 global block [r][k] (a block inverse D) streamed through
+// `stages`; G is a shared 128x128 tile stored [k][n] (stride LDS), complete and visible to the CTA.
 __device__ __forceinline__ void epi_product_DxG(Acc& out, const double* __restrict__ Dm, const double* G,
                                                 double* stages, Ring& ring, const ThreadCoord& tc) {
-    const int oa = (tc.wm * 64 + tc.g) * LDT + tc.c;
+    const int oa = (tc.wm * 8 + tc.g) * LDT + tc.c;
     ring_pipeline(
         ring, TB / BK, [&](int st, int kt) { stage_slice(stages + st * STAGE_DBL, Dm + kt * BK, TB, tc.tid); },
         [&](int st, int kt, auto half) {
             constexpr int H = decltype(half)::value;
             const double* sa = stages + st * STAGE_DBL + oa;
-            // B fragment: element (k = kt*16 + ks*4 + c, n = wn*32 + ni*8 + g) of G[k][n]
-            const double* sb = G + (kt * BK + tc.c) * LDS + tc.wn * 32 + tc.g;
+            // B fragment: element (k = kt*16 + ks*4 + c, n = cgroup(ni)*8 + g) of G[k][n]
+            const double* sb = G + (kt * BK + tc.c) * LDS + tc.wn * 8 + tc.g;
+            auto body = [&](auto mi0) {     // rows of Dm with k <= r only: row groups mi >= kt
+                constexpr int MI0 = decltype(mi0)::value;
 #pragma unroll
-            for (int ks = H * (BK / 8); ks < (H + 1) * (BK / 8); ++ks) {
-                double a[8], b[4];
+                for (int ks = H * (BK / 8); ks < (H + 1) * (BK / 8); ++ks) {
+                    double a[8], b[4];
 #pragma unroll
-                for (int mi = 0; mi < 8; ++mi) a[mi] = sa[mi * 8 * LDT + ks * 4];
+                    for (int mi = MI0; mi < 8; ++mi) a[mi] = sa[mi * FRAG_A_STEP * LDT + ks * 4];
 #pragma unroll
-                for (int ni = 0; ni < 4; ++ni) b[ni] = sb[ks * 4 * LDS + ni * 8];
+                    for (int ni = 0; ni < 4; ++ni) b[ni] = sb[ks * 4 * LDS + ni * FRAG_B_STEP];
 #pragma unroll
-                for (int mi = 0; mi < 8; ++mi)
+                    for (int mi = MI0; mi < 8; ++mi)
 #pragma unroll
-                    for (int ni = 0; ni < 4; ++ni) dmma884(out.v[mi][ni], a[mi], b[ni]);
+                        for (int ni = 0; ni < 4; ++ni) dmma884(out.v[mi][ni], a[mi], b[ni]);
+                }
+            };
+            switch (kt) {
+                case 0: body(std::integral_constant<int, 0>{}); break;
+                case 1: body(std::integral_constant<int, 1>{}); break;
+                case 2: body(std::integral_constant<int, 2>{}); break;
+                case 3: body(std::integral_constant<int, 3>{}); break;
+                case 4: body(std::integral_constant<int, 4>{}); break;
+                case 5: body(std::integral_constant<int, 5>{}); break;
+                case 6: body(std::integral_constant<int, 6>{}); break;
+                default: body(std::integral_constant<int, 7>{}); break;
             }
         });
 }
