@@ -317,7 +317,7 @@ def main():
         dist.destroy_process_group()
 
 
-def fit_sample(ctx, m, r=2, S=32):
+def fit_sample(ctx, m, r=4, S=32):
     """Measured GP fits/s on a bounded sub-workload: r modes x S starts, full L-BFGS-B + posterior moments."""
     T, Y, _, gp_of = workload(r, m, S, seed=123)
     b = np.log(np.array([(1e-5, 1e5), (1e-5, 1e2), (1e-16, 1e2)]))
@@ -367,11 +367,11 @@ def assembly_roofline(ctx, dev, n=8192, B=8):
 
 
 def fit_reference_configs(ctx):
-    """Full step2 fit (all 101 starts per GP, the reference's own start points) + posterior moments on the three
-    reference experiment configurations (tests/golden/*.npz), with the reference's CPU wall time recorded when the
+    """Full step2 fit (all 101 starts per GP, the reference's own start points) + posterior moments on four of the
+    reference's experiment configurations (tests/golden/*.npz), with the reference's CPU wall time recorded when the
     fixtures were generated (8-core build container) beside it."""
     out = {}
-    for name in ("seird_090_090_10_360", "heat_1_20_05_80_5", "euler_006_200_03_400_6"):
+    for name in ("seird_090_090_10_360", "seird_120_010_05_480", "heat_1_20_05_80_5", "euler_006_200_03_400_6"):
         g = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"), allow_pickle=False)
         T, Y, t_est = g["T"], g["Y"], g["t_est"]
         G = T.shape[0]

@@ -24,7 +24,7 @@ EXPORTS = (
     "gpbo_wave_capacity", "gpbo_assemble", "gpbo_lml_grad", "gpbo_lml_grad_host", "gpbo_fit_host",
     "gpbo_predict_host", "gpbo_lstsq_moments_host", "gpbo_lstsq_moments", "gpbo_profile_enable",
     "gpbo_profile_get", "gpbo_bench_dmma_peak", "gpbo_lbfgsb_minimize", "gpbo_sqrtw", "gpbo_sqrtw_host",
-    "gpbo_lstsq_weights_host",
+    "gpbo_lstsq_weights_host", "gpbo_assemble_matern",
 )
 
 
@@ -58,6 +58,8 @@ def load():
     lib.gpbo_launch_count.restype = C.c_longlong
     lib.gpbo_wave_capacity.argtypes = [vp, C.c_int]
     lib.gpbo_assemble.argtypes = [vp, C.c_int, vp, C.c_long, C.c_int, vp, C.c_long, C.c_int, vp, C.c_int, vp, vp]
+    lib.gpbo_assemble_matern.argtypes = [vp, C.c_int, C.c_int, vp, C.c_long, C.c_int, vp, C.c_long, C.c_int, vp, C.c_int,
+                                         vp, vp]
     lib.gpbo_lml_grad.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, vp, vp]
     lib.gpbo_lml_grad_host.argtypes = [vp, dp, dp, C.c_int, C.c_int, dp, ip, C.c_int, dp, dp, ip]
     lib.gpbo_fit_host.argtypes = [vp, dp, dp, C.c_int, C.c_int, dp, dp, ip, C.c_int, dp, dp, dp, ip, ip, ip,
@@ -251,7 +253,14 @@ class Context:
         return state, ddt, cov, w, st, wst, wit
 
     # -- device-pointer entry points (torch tensors are only address carriers) ------------
-    def assemble_device(self, kind, t1_ptr, t1_stride, n1, t2_ptr, t2_stride, n2, theta_ptr, B, out_ptr, stream=0):
+    def assemble_device(self, kind, t1_ptr, t1_stride, n1, t2_ptr, t2_stride, n2, theta_ptr, B, out_ptr, stream=0,
+                        twice_nu=0):
+        """twice_nu = 0: RBF (gpbo_assemble); 3 / 5: Matern nu = 3/2, 5/2 (gpbo_assemble_matern)."""
+        if twice_nu:
+            _check(self._lib.gpbo_assemble_matern(self._h, int(twice_nu), int(kind), t1_ptr, int(t1_stride), int(n1),
+                                                  t2_ptr, int(t2_stride), int(n2), theta_ptr, int(B), out_ptr, stream),
+                   "gpbo_assemble_matern")
+            return
         _check(self._lib.gpbo_assemble(self._h, int(kind), t1_ptr, int(t1_stride), int(n1), t2_ptr, int(t2_stride),
                                        int(n2), theta_ptr, int(B), out_ptr, stream), "gpbo_assemble")
 

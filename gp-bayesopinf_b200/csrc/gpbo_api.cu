@@ -153,9 +153,12 @@ MatArgs mat_args(gpbo_ctx* c, int m, int m_pad) {
     return a;
 }
 
-bool g_attr_done = false;
+// cudaFuncSetAttribute is per device: remember which devices have been configured
+bool g_attr_done[64] = {false};
 int set_kernel_attrs() {
-    if (g_attr_done) return GPBO_OK;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && g_attr_done[dev]) return GPBO_OK;
     CUDA_TRY(cudaFuncSetAttribute(chol_diag_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(chol_diag_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(chol_panel_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
@@ -166,17 +169,19 @@ int set_kernel_attrs() {
     CUDA_TRY(cudaFuncSetAttribute(lauum_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(ns_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
-#define GPBO_SYM_ATTR(K) CUDA_TRY(cudaFuncSetAttribute(assemble_sym_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, SYM_SMEM));
-    GPBO_SYM_ATTR(0) GPBO_SYM_ATTR(1) GPBO_SYM_ATTR(2) GPBO_SYM_ATTR(3) GPBO_SYM_ATTR(4) GPBO_SYM_ATTR(5) GPBO_SYM_ATTR(6)
+#define GPBO_SYM_ATTR(F, K) CUDA_TRY(cudaFuncSetAttribute(assemble_sym_kernel<F, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, SYM_SMEM));
+#define GPBO_SYM_ATTR_F(F) GPBO_SYM_ATTR(F, 0) GPBO_SYM_ATTR(F, 1) GPBO_SYM_ATTR(F, 2) GPBO_SYM_ATTR(F, 3) GPBO_SYM_ATTR(F, 4) GPBO_SYM_ATTR(F, 5) GPBO_SYM_ATTR(F, 6)
+    GPBO_SYM_ATTR_F(0) GPBO_SYM_ATTR_F(3) GPBO_SYM_ATTR_F(5)
+#undef GPBO_SYM_ATTR_F
 #undef GPBO_SYM_ATTR
-    g_attr_done = true;
+    if (dev >= 0 && dev < 64) g_attr_done[dev] = true;
     return GPBO_OK;
 }
 
 // Split-K policy: with fewer than ~one CTA per SM in a launch whose tiles run a k-loop of nk_max slices, the loop
 // is cut into up to 16 chunks of >= 4 slices computed by separate CTAs (splitk_partial_kernel) first.
 // Returns a PreAcc with buf == nullptr when the fused kernels should run their own loop.
-int g_sm_count = 0;
+int g_sm_count = 0;   // one process drives one GPU model: the SM count is the same on every device of a box
 int plan_split(gpbo_ctx* c, cudaStream_t s, const MatArgs& a, int mode, int idx, int nb, int ntile, int nk_max,
                const double* X, long x_stride, PreAcc* out) {
     out->buf = nullptr; out->nsplit = 1; out->chunk = nk_max;
@@ -456,32 +461,46 @@ int gpbo_profile_get(gpbo_ctx* c, double* ms, long long* launches) {
     return GPBO_OK;
 }
 
-int gpbo_assemble(gpbo_ctx* c, int kind, const double* t1, long t1_stride, int n1, const double* t2, long t2_stride,
-                  int n2, const double* theta, int B, double* out, void* stream) {
+static int assemble_impl(gpbo_ctx* c, int fam, int kind, const double* t1, long t1_stride, int n1, const double* t2,
+                         long t2_stride, int n2, const double* theta, int B, double* out, void* stream) {
     if (!c || !t1 || !t2 || !theta || !out || n1 <= 0 || n2 <= 0 || B <= 0 || kind < 0 || kind > 6)
         return fail(GPBO_EINVAL, "assemble: bad argument");
+    if (fam != 0 && fam != 3 && fam != 5) return fail(GPBO_EINVAL, "assemble: twice_nu must be 3 or 5");
     CUDA_TRY(cudaSetDevice(c->device));
     if (int rc = set_kernel_attrs()) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const long os = (long)n1 * n2;
     const bool sym = (t1 == t2 && t1_stride == t2_stride && n1 == n2);
     launch(c, C_ASM, s, [&] {
-        if (sym) {
-            const int nt = (n1 + SYM_T - 1) / SYM_T;
-            dim3 grid(nt * (nt + 1) / 2, B);
-#define GPBO_ASM_SYM(K) case K: assemble_sym_kernel<K><<<grid, NTHR, SYM_SMEM, s>>>(t1, t1_stride, n1, theta, out, os); break;
-            switch (kind) { GPBO_ASM_SYM(0) GPBO_ASM_SYM(1) GPBO_ASM_SYM(2) GPBO_ASM_SYM(3) GPBO_ASM_SYM(4) GPBO_ASM_SYM(5) GPBO_ASM_SYM(6) }
-#undef GPBO_ASM_SYM
-        } else {
-            dim3 grid((n2 + ASM_COLS - 1) / ASM_COLS, (n1 + ASM_ROWS - 1) / ASM_ROWS, B);
-#define GPBO_ASM_GEN(K) case K: assemble_general_kernel<K><<<grid, NTHR, 0, s>>>(t1, t1_stride, n1, t2, t2_stride, n2, theta, out, os); break;
-            switch (kind) { GPBO_ASM_GEN(0) GPBO_ASM_GEN(1) GPBO_ASM_GEN(2) GPBO_ASM_GEN(3) GPBO_ASM_GEN(4) GPBO_ASM_GEN(5) GPBO_ASM_GEN(6) }
-#undef GPBO_ASM_GEN
-        }
+        const int nt = (n1 + SYM_T - 1) / SYM_T;
+        dim3 gs(nt * (nt + 1) / 2, B);
+        dim3 gg((n2 + ASM_COLS - 1) / ASM_COLS, (n1 + ASM_ROWS - 1) / ASM_ROWS, B);
+#define GPBO_ASM_CASE(F, K)                                                                                              \
+    case K:                                                                                                              \
+        if (sym) assemble_sym_kernel<F, K><<<gs, NTHR, SYM_SMEM, s>>>(t1, t1_stride, n1, theta, out, os);                \
+        else assemble_general_kernel<F, K><<<gg, NTHR, 0, s>>>(t1, t1_stride, n1, t2, t2_stride, n2, theta, out, os);    \
+        break;
+#define GPBO_ASM_FAM(F)                                                                                                  \
+    switch (kind) { GPBO_ASM_CASE(F, 0) GPBO_ASM_CASE(F, 1) GPBO_ASM_CASE(F, 2) GPBO_ASM_CASE(F, 3) GPBO_ASM_CASE(F, 4)   \
+                    GPBO_ASM_CASE(F, 5) GPBO_ASM_CASE(F, 6) }
+        if (fam == 0) { GPBO_ASM_FAM(0) } else if (fam == 3) { GPBO_ASM_FAM(3) } else { GPBO_ASM_FAM(5) }
+#undef GPBO_ASM_FAM
+#undef GPBO_ASM_CASE
     });
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(s));
     return GPBO_OK;
+}
+
+int gpbo_assemble(gpbo_ctx* c, int kind, const double* t1, long t1_stride, int n1, const double* t2, long t2_stride,
+                  int n2, const double* theta, int B, double* out, void* stream) {
+    return assemble_impl(c, 0, kind, t1, t1_stride, n1, t2, t2_stride, n2, theta, B, out, stream);
+}
+
+int gpbo_assemble_matern(gpbo_ctx* c, int twice_nu, int kind, const double* t1, long t1_stride, int n1, const double* t2,
+                         long t2_stride, int n2, const double* theta, int B, double* out, void* stream) {
+    if (twice_nu != 3 && twice_nu != 5) return fail(GPBO_EINVAL, "assemble_matern: twice_nu must be 3 or 5");
+    return assemble_impl(c, twice_nu, kind, t1, t1_stride, n1, t2, t2_stride, n2, theta, B, out, stream);
 }
 
 int gpbo_lml_grad(gpbo_ctx* c, const double* t, const double* y, int G, int m, const double* theta, const int* gp_of,

@@ -141,27 +141,56 @@ struct AsmConsts {
     }
 };
 
-template <int KIND>
+// FAM 0: RBF (the reference's kernel).  FAM 3 / 5: Matern nu = 3/2 / 5/2 -- an extension (the reference has no
+// Matern kernel; BASELINE.json's north star names "RBF/Matern kernel-matrix assembly"): K follows scikit-learn's
+// Matern (kernels.py:1601-1790: dists = |x1 - x2| with x = t / ell, K = dists * sqrt(2 nu), ...), the derivative
+// cross-covariances are the analytic d/dt1 and d^2/dt1 dt2 of the same kernel.  Matern kinds 1 / 3 alias 0 / 2.
+template <int FAM, int KIND>
 __device__ __forceinline__ double assemble_element(const AsmConsts& k, bool diag, double x1, double x2) {
-    const double d = x1 - x2;
-    const double d2 = d * d;
-    if (KIND == 0) return diag ? k.sig2 + k.chi : k.sig2 * gpbo_exp(-0.5 * d2);
-    if (KIND == 1) return diag ? k.sig2 + k.chi : k.sig2 * gpbo_exp(-gpbo_div(d2, k.two_ell2, k.r_two_ell2));
-    if (KIND == 2) return k.sig2 * gpbo_exp(-0.5 * d2);
-    if (KIND == 6) return k.sig2 * (gpbo_exp(-0.5 * d2) * d2);
-    const double kap = k.sig2 * gpbo_exp(-gpbo_div(d2, k.two_ell2, k.r_two_ell2));
-    if (KIND == 3) return kap;
-    if (KIND == 4) return gpbo_div(-d * kap, k.ell2, k.r_ell2);
-    return gpbo_div((1 - gpbo_div(d2, k.ell2, k.r_ell2)) * kap, k.ell2, k.r_ell2);
+    if (FAM == 0) {
+        const double d = x1 - x2;
+        const double d2 = d * d;
+        if (KIND == 0) return diag ? k.sig2 + k.chi : k.sig2 * gpbo_exp(-0.5 * d2);
+        if (KIND == 1) return diag ? k.sig2 + k.chi : k.sig2 * gpbo_exp(-gpbo_div(d2, k.two_ell2, k.r_two_ell2));
+        if (KIND == 2) return k.sig2 * gpbo_exp(-0.5 * d2);
+        if (KIND == 6) return k.sig2 * (gpbo_exp(-0.5 * d2) * d2);
+        const double kap = k.sig2 * gpbo_exp(-gpbo_div(d2, k.two_ell2, k.r_two_ell2));
+        if (KIND == 3) return kap;
+        if (KIND == 4) return gpbo_div(-d * kap, k.ell2, k.r_ell2);
+        return gpbo_div((1 - gpbo_div(d2, k.ell2, k.r_ell2)) * kap, k.ell2, k.r_ell2);
+    } else {
+        // x1, x2 are t / ell for every Matern kind
+        const double dx = x1 - x2;
+        const double dist = fabs(dx);
+        const double c = (FAM == 3) ? 1.7320508075688772 : 2.23606797749979;      // sqrt(2 nu)
+        const double K = dist * c;
+        const double e = gpbo_exp(-K);
+        if (KIND == 0 || KIND == 1) {
+            if (diag) return k.sig2 + k.chi;
+            return k.sig2 * ((FAM == 3) ? (1.0 + K) * e : (1.0 + K + K * K / 3.0) * e);
+        }
+        if (KIND == 2 || KIND == 3) return k.sig2 * ((FAM == 3) ? (1.0 + K) * e : (1.0 + K + K * K / 3.0) * e);
+        if (KIND == 6) {   // dK / dlog(ell): kernels.py (nu = 1.5: 3 D exp(-sqrt(3 D)); nu = 2.5: 5/3 D (tmp + 1) exp(-tmp))
+            const double D = dx * dx;
+            return k.sig2 * ((FAM == 3) ? 3.0 * D * e : 5.0 / 3.0 * D * (K + 1.0) * e);
+        }
+        // derivatives with respect to the unscaled times: tau = ell * dx, a = c / ell, a^2 = 2 nu / ell^2
+        const double a2 = (FAM == 3 ? 3.0 : 5.0) * k.r_ell2;
+        const double tau = dx * k.ell;
+        if (KIND == 4)    // d k / d t1
+            return (FAM == 3) ? -k.sig2 * a2 * tau * e : -k.sig2 * (a2 / 3.0) * tau * (1.0 + K) * e;
+        // KIND 5: d^2 k / d t1 d t2 = - k''(tau)
+        return (FAM == 3) ? k.sig2 * a2 * (1.0 - K) * e : k.sig2 * (a2 / 3.0) * (1.0 + K - K * K) * e;
+    }
 }
 
-template <int KIND>
-struct AsmScaled { static constexpr bool value = (KIND == 0 || KIND == 2 || KIND == 6); };
+template <int FAM, int KIND>
+struct AsmScaled { static constexpr bool value = (FAM != 0) || (KIND == 0 || KIND == 2 || KIND == 6); };
 
 constexpr int ASM_ROWS = 32;     // rows per CTA of the general kernel
 constexpr int ASM_COLS = 2 * NTHR;
 
-template <int KIND>
+template <int FAM, int KIND>
 __global__ void __launch_bounds__(NTHR)
 assemble_general_kernel(const double* __restrict__ t1, long t1_stride, int n1, const double* __restrict__ t2,
                         long t2_stride, int n2, const double* __restrict__ theta, double* __restrict__ out,
@@ -169,7 +198,7 @@ assemble_general_kernel(const double* __restrict__ t1, long t1_stride, int n1, c
     __shared__ double x1s[ASM_ROWS];
     const int p = blockIdx.z;
     const AsmConsts k(theta + 3 * p);
-    constexpr bool scaled = AsmScaled<KIND>::value;
+    constexpr bool scaled = AsmScaled<FAM, KIND>::value;
     const int c0 = blockIdx.x * ASM_COLS + 2 * threadIdx.x;
     const int r0 = blockIdx.y * ASM_ROWS;
     const double* a1 = t1 + (long)p * t1_stride;
@@ -192,8 +221,8 @@ assemble_general_kernel(const double* __restrict__ t1, long t1_stride, int n1, c
     for (int rr = 0; rr < nr; ++rr) {
         const int r = r0 + rr;
         const double x1 = x1s[rr];
-        const double va = assemble_element<KIND>(k, r == c0, x1, x2a);
-        const double vb = assemble_element<KIND>(k, r == c0 + 1, x1, x2b);
+        const double va = assemble_element<FAM, KIND>(k, r == c0, x1, x2a);
+        const double vb = assemble_element<FAM, KIND>(k, r == c0 + 1, x1, x2b);
         if (vec) {
             *reinterpret_cast<double2*>(o + (long)r * n2 + c0) = make_double2(va, vb);
         } else {
@@ -207,7 +236,7 @@ constexpr int SYM_T = 64;            // tile edge of the symmetric kernel
 constexpr int SYM_LD = SYM_T + 1;    // odd stride: conflict-free row and column access
 constexpr int SYM_SMEM = (2 * SYM_T * SYM_LD + 2 * SYM_T) * 8;   // 67584 B -> 3 CTAs / SM
 
-template <int KIND>
+template <int FAM, int KIND>
 __global__ void __launch_bounds__(NTHR)
 assemble_sym_kernel(const double* __restrict__ t, long t_stride, int n, const double* __restrict__ theta,
                     double* __restrict__ out, long out_stride) {
@@ -222,7 +251,7 @@ assemble_sym_kernel(const double* __restrict__ t, long t_stride, int n, const do
     while (I * (I + 1) / 2 > q) --I;
     const int J = q - I * (I + 1) / 2;
     const AsmConsts k(theta + 3 * p);
-    constexpr bool scaled = AsmScaled<KIND>::value;
+    constexpr bool scaled = AsmScaled<FAM, KIND>::value;
     const double* a = t + (long)p * t_stride;
     const int tid = threadIdx.x;
     if (tid < 2 * SYM_T) {
@@ -241,7 +270,7 @@ assemble_sym_kernel(const double* __restrict__ t, long t_stride, int n, const do
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int r = ty + 16 * i, c = tx + 16 * j;
-            const double v = assemble_element<KIND>(k, I == J && r == c, x1[i], x2[j]);
+            const double v = assemble_element<FAM, KIND>(k, I == J && r == c, x1[i], x2[j]);
             S[r * SYM_LD + c] = v;
             if (I != J) ST[c * SYM_LD + r] = (KIND == 4) ? -v : v;
         }

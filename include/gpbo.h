@@ -60,6 +60,14 @@ int gpbo_wave_capacity(gpbo_ctx* ctx, int m);
 int gpbo_assemble(gpbo_ctx* ctx, int kind, const double* t1, long t1_stride, int n1, const double* t2,
                   long t2_stride, int n2, const double* theta, int B, double* out, void* stream);
 
+/* Matern (nu = twice_nu / 2, twice_nu = 3 or 5) counterpart of gpbo_assemble -- an extension: the reference has no
+ * Matern kernel (BASELINE.json's north star names RBF/Matern assembly).  K follows scikit-learn's Matern
+ * (kernels.py:1601-1790) in (ConstantKernel * Matern) + WhiteKernel; same arguments and kinds as gpbo_assemble
+ * (kinds 1 / 3 alias 0 / 2; 4 = d k / d t1; 5 = d^2 k / d t1 d t2; 6 = dK / dlog(ell)). */
+int gpbo_assemble_matern(gpbo_ctx* ctx, int twice_nu, int kind, const double* t1, long t1_stride, int n1,
+                         const double* t2, long t2_stride, int n2, const double* theta, int B, double* out,
+                         void* stream);
+
 /* Batched log-marginal likelihood and gradient at fixed theta.
  * Replaces GaussianProcessRegressor.log_marginal_likelihood(theta, eval_gradient=True)
  * (sklearn _gpr.py:541-656) for B pairs at once.

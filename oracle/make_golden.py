@@ -248,6 +248,8 @@ ALL = dict(
     seird=lambda: make_config("seird_090_090_10_360", data_seird),
     heat=lambda: make_config("heat_1_20_05_80_5", data_heat),
     euler=lambda: make_config("euler_006_200_03_400_6", data_euler),
+    # sparse-data line of ODEs/experiments.sh (`main.py 120 010 .05 480`): only 10 samples per state
+    seird_sparse=lambda: make_config("seird_120_010_05_480", lambda: data_seird(10, 0.05, 480, 120)),
 )
 
 if __name__ == "__main__":

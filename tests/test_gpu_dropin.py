@@ -145,3 +145,20 @@ def test_fit_gaussian_processes_batched(pkg, flavour, monkeypatch, capsys):
         assert rel(gp.state_estimate, g["state_estimate"][i]) <= 1e-4
         assert rel(gp.ddt_estimate, g["ddt_estimate"][i]) <= 1e-3
         assert gp.sqrtW.shape == (t_est.size, t_est.size)
+
+
+def test_sharded_step2_over_nccl():
+    """Sharded fit + moments on 2 GPUs over NCCL (skipped on a single-GPU box; the CPU twin of this test is
+    tests/test_sharding_gloo.py)."""
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from conftest import ROOT
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "tools", "multi_gpu_fit.py")]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]

@@ -228,6 +228,58 @@ def test_assemble_symmetric_path(ctx, n):
             assert np.all(np.abs(got[p] - ref) <= 1e-15 * np.abs(ref) + 1e-300 * max(1.0, np.abs(ref).max())), (kind, p)
 
 
+@pytest.mark.parametrize("twice_nu", [3, 5])
+@pytest.mark.parametrize("same", [False, True])
+def test_assemble_matern(ctx, twice_nu, same):
+    """Matern extension of the assembly (the reference has no Matern kernel): K and dK/dlog(ell) against
+    scikit-learn's (ConstantKernel * Matern) + WhiteKernel, the derivative cross-covariances against the analytic
+    formulas and against central differences of the kernel itself."""
+    import torch
+    from sklearn.gaussian_process.kernels import ConstantKernel, Matern, WhiteKernel
+
+    nu = twice_nu / 2
+    rng = np.random.default_rng(twice_nu)
+    n1, n2 = (150, 150) if same else (97, 61)
+    t1 = np.sort(rng.uniform(0, 1, n1))
+    t2 = t1 if same else np.sort(rng.uniform(0, 1, n2))
+    s2, ell, chi = 1.7, 0.13, 4e-3
+    theta = np.log(np.array([[s2, ell, chi]]))
+    dev = torch.device("cuda", 0)
+    a, th = torch.as_tensor(t1, device=dev), torch.as_tensor(theta, device=dev)
+    b = a if same else torch.as_tensor(t2, device=dev)
+    out = torch.empty((1, n1, n2), dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+
+    def run(kind):
+        ctx.assemble_device(kind, a.data_ptr(), 0, n1, b.data_ptr(), 0, n2, th.data_ptr(), 1, out.data_ptr(), 0,
+                            twice_nu=twice_nu)
+        return out.cpu().numpy()[0].copy()
+
+    kern = ConstantKernel(s2) * Matern(length_scale=ell, nu=nu) + WhiteKernel(chi)
+    cross = kern(t1[:, None], t2[:, None])                        # White(X, Y) = 0
+    assert rel(run(2), cross) <= 1e-14 and rel(run(3), cross) <= 1e-14
+    if same:
+        Kref, dK = kern(t1[:, None], eval_gradient=True)
+        assert rel(run(0), Kref) <= 1e-14 and rel(run(1), Kref) <= 1e-14
+        assert rel(run(6), dK[:, :, 1]) <= 1e-13              # theta order: constant, length scale, noise
+    # derivative cross-covariances: analytic, and finite differences of the kernel
+    tau = t1[:, None] - t2[None, :]
+    aa = np.sqrt(twice_nu) / ell
+    e = np.exp(-aa * np.abs(tau))
+    if twice_nu == 3:
+        k1 = -s2 * aa**2 * tau * e
+        k2 = s2 * aa**2 * (1 - aa * np.abs(tau)) * e
+    else:
+        k1 = -s2 * aa**2 / 3 * tau * (1 + aa * np.abs(tau)) * e
+        k2 = s2 * aa**2 / 3 * (1 + aa * np.abs(tau) - (aa * tau) ** 2) * e
+    assert rel(run(4), k1) <= 1e-13 and rel(run(5), k2) <= 1e-13
+    km = ConstantKernel(s2) * Matern(length_scale=ell, nu=nu)
+    h = 1e-6
+    fd1 = (km((t1 + h)[:, None], t2[:, None]) - km((t1 - h)[:, None], t2[:, None])) / (2 * h)
+    mask = np.abs(tau) > 10 * h                                   # nu = 3/2 has a kink in dk/dtau at tau = 0
+    assert np.abs(fd1 - k1)[mask].max() <= 1e-6 * np.abs(k1).max()
+
+
 # ------------------------------------------------------------------ posterior moments
 @pytest.mark.parametrize("name", REAL_CONFIGS)
 def test_predict_and_lstsq_moments_golden(ctx, name):
