@@ -12,7 +12,7 @@ Public surface (mirrors the reference):
 
 from . import _lib, gpkernels, sharding, step2_fitgps  # noqa: F401
 from ._lib import Context, GpboError, default_context  # noqa: F401
-from .gpkernels import GP_RBFW  # noqa: F401
+from .gpkernels import GP_MaternW, GP_RBFW  # noqa: F401
 from .step2_fitgps import fit_gaussian_processes, fit_gaussian_processes_multi  # noqa: F401
 
 __version__ = "0.1.0"

@@ -24,7 +24,7 @@ EXPORTS = (
     "gpbo_wave_capacity", "gpbo_assemble", "gpbo_lml_grad", "gpbo_lml_grad_host", "gpbo_fit_host",
     "gpbo_predict_host", "gpbo_lstsq_moments_host", "gpbo_lstsq_moments", "gpbo_profile_enable",
     "gpbo_profile_get", "gpbo_bench_dmma_peak", "gpbo_lbfgsb_minimize", "gpbo_sqrtw", "gpbo_sqrtw_host",
-    "gpbo_lstsq_weights_host", "gpbo_assemble_matern",
+    "gpbo_lstsq_weights_host", "gpbo_assemble_matern", "gpbo_set_kernel_family",
 )
 
 
@@ -57,6 +57,7 @@ def load():
     lib.gpbo_launch_count.argtypes = [vp]
     lib.gpbo_launch_count.restype = C.c_longlong
     lib.gpbo_wave_capacity.argtypes = [vp, C.c_int]
+    lib.gpbo_set_kernel_family.argtypes = [vp, C.c_int]
     lib.gpbo_assemble.argtypes = [vp, C.c_int, vp, C.c_long, C.c_int, vp, C.c_long, C.c_int, vp, C.c_int, vp, vp]
     lib.gpbo_assemble_matern.argtypes = [vp, C.c_int, C.c_int, vp, C.c_long, C.c_int, vp, C.c_long, C.c_int, vp, C.c_int,
                                          vp, vp]
@@ -128,6 +129,10 @@ class Context:
     @property
     def launch_count(self) -> int:
         return int(self._lib.gpbo_launch_count(self._h))
+
+    def set_kernel_family(self, twice_nu: int = 0):
+        """0: RBF (the reference); 3 / 5: Matern nu = 3/2, 5/2.  Applies to all later calls on this context."""
+        _check(self._lib.gpbo_set_kernel_family(self._h, int(twice_nu)), "gpbo_set_kernel_family")
 
     def wave_capacity(self, m: int) -> int:
         return int(self._lib.gpbo_wave_capacity(self._h, int(m)))

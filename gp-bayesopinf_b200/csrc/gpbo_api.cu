@@ -51,6 +51,7 @@ struct ProfRec { int cls; cudaEvent_t e0, e1; };
 
 struct gpbo_ctx {
     int device = 0;
+    int family = 0;                  // 0 RBF (the reference's kernel); 3 / 5: Matern nu = 3/2, 5/2
     size_t limit = 0;
     cudaStream_t stream = nullptr;   // used by the *_host entry points
     long long launches = 0;
@@ -161,12 +162,18 @@ int set_kernel_attrs() {
     if (dev >= 0 && dev < 64 && g_attr_done[dev]) return GPBO_OK;
     CUDA_TRY(cudaFuncSetAttribute(chol_diag_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(chol_diag_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(chol_diag_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(chol_diag_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(chol_panel_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(chol_panel_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(lauum_grad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(lauum_grad_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(chol_panel_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(chol_panel_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(chol_panel_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(trtri_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(splitk_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
-    CUDA_TRY(cudaFuncSetAttribute(lauum_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(lauum_grad_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(ns_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
 #define GPBO_SYM_ATTR(F, K) CUDA_TRY(cudaFuncSetAttribute(assemble_sym_kernel<F, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, SYM_SMEM));
@@ -206,27 +213,34 @@ int plan_split(gpbo_ctx* c, cudaStream_t s, const MatArgs& a, int mode, int idx,
     return GPBO_OK;
 }
 
-// Factor K(theta) for nb pairs and solve for alpha.  order: 0 sklearn, 1 rbf_eval.
+// Factor K(theta) for nb pairs and solve for alpha.  order: 0 sklearn, 1 rbf_eval (RBF only; Matern always uses the
+// scaled sklearn order).
 int factor_wave(gpbo_ctx* c, cudaStream_t s, const MatArgs& a, const double* t_dev, const double* ypad,
                 const double* theta_dev, const int* gpof_dev, int nb, int order) {
+    const int gen = c->family == 0 ? order : (c->family == 3 ? 2 : 3);     // element generator (AsmSelect index)
+    if (c->family != 0) order = 0;
     launch(c, C_PREP, s, [&] {
         prep_pairs_kernel<<<nb, 256, 0, s>>>(theta_dev, gpof_dev, t_dev, a.m, a.lda, order, c->pp.as<PairParams>(),
                                              c->ts.as<double>(), c->status.as<int>());
     });
-    CrossArgs none{nullptr, 0, 0, 0};
+    CrossArgs none{nullptr, 0, 0, 0, 0};
     for (int j = 0; j < a.T; ++j) {
         PreAcc pre;
         int rc = plan_split(c, s, a, 0, j, nb, a.T - j, j * (TB / BK), nullptr, 0, &pre);
         if (rc) return rc;
         launch(c, C_DIAG, s, [&] {
-            if (order == 0) chol_diag_kernel<0><<<nb, NTHR, MAIN_SMEM, s>>>(a, j, pre);
-            else chol_diag_kernel<1><<<nb, NTHR, MAIN_SMEM, s>>>(a, j, pre);
+            if (gen == 0) chol_diag_kernel<0><<<nb, NTHR, MAIN_SMEM, s>>>(a, j, pre);
+            else if (gen == 1) chol_diag_kernel<1><<<nb, NTHR, MAIN_SMEM, s>>>(a, j, pre);
+            else if (gen == 2) chol_diag_kernel<2><<<nb, NTHR, MAIN_SMEM, s>>>(a, j, pre);
+            else chol_diag_kernel<3><<<nb, NTHR, MAIN_SMEM, s>>>(a, j, pre);
         });
         if (j < a.T - 1) {
             const int grid = nb * (a.T - 1 - j);
             launch(c, C_PANEL, s, [&] {
-                if (order == 0) chol_panel_kernel<0, false><<<grid, NTHR, TILE_SMEM, s>>>(a, j, nullptr, 0, 0, none, pre);
-                else chol_panel_kernel<1, false><<<grid, NTHR, TILE_SMEM, s>>>(a, j, nullptr, 0, 0, none, pre);
+                if (gen == 0) chol_panel_kernel<0, false><<<grid, NTHR, TILE_SMEM, s>>>(a, j, nullptr, 0, 0, none, pre);
+                else if (gen == 1) chol_panel_kernel<1, false><<<grid, NTHR, TILE_SMEM, s>>>(a, j, nullptr, 0, 0, none, pre);
+                else if (gen == 2) chol_panel_kernel<2, false><<<grid, NTHR, TILE_SMEM, s>>>(a, j, nullptr, 0, 0, none, pre);
+                else chol_panel_kernel<3, false><<<grid, NTHR, TILE_SMEM, s>>>(a, j, nullptr, 0, 0, none, pre);
             });
         }
     }
@@ -251,7 +265,12 @@ int eval_wave(gpbo_ctx* c, cudaStream_t s, const double* t_dev, const double* yp
             launch(c, C_TRTRI, s, [&] { trtri_row_kernel<<<nb * i, NTHR, TILE_SMEM, s>>>(a, i, pre); });
         }
         launch(c, C_LAUUM, s, [&] {
-            lauum_grad_kernel<<<nb * ntiles, NTHR, MAIN_SMEM, s>>>(a, c->alpha.as<double>(), c->part.as<double>(), ntiles);
+            if (c->family == 0)
+                lauum_grad_kernel<0><<<nb * ntiles, NTHR, MAIN_SMEM, s>>>(a, c->alpha.as<double>(), c->part.as<double>(), ntiles);
+            else if (c->family == 3)
+                lauum_grad_kernel<3><<<nb * ntiles, NTHR, MAIN_SMEM, s>>>(a, c->alpha.as<double>(), c->part.as<double>(), ntiles);
+            else
+                lauum_grad_kernel<5><<<nb * ntiles, NTHR, MAIN_SMEM, s>>>(a, c->alpha.as<double>(), c->part.as<double>(), ntiles);
         });
     }
     launch(c, C_FINAL, s, [&] {
@@ -428,6 +447,14 @@ int gpbo_destroy(gpbo_ctx* c) {
 }
 
 long long gpbo_launch_count(const gpbo_ctx* c) { return c ? c->launches : 0; }
+
+int gpbo_set_kernel_family(gpbo_ctx* c, int twice_nu) {
+    if (!c) return fail(GPBO_EINVAL, "set_kernel_family: ctx is NULL");
+    if (twice_nu != 0 && twice_nu != 3 && twice_nu != 5)
+        return fail(GPBO_EINVAL, "set_kernel_family: 0 (RBF), 3 (Matern-3/2) or 5 (Matern-5/2)");
+    c->family = twice_nu;
+    return GPBO_OK;
+}
 
 int gpbo_wave_capacity(gpbo_ctx* c, int m) {
     if (!c || m <= 0) return fail(GPBO_EINVAL, "wave_capacity: bad argument");
@@ -699,7 +726,7 @@ static int moments_device(gpbo_ctx* c, cudaStream_t s, int mode, const double* t
     }
     rc = make_ypad(c, s, y, G, m, m_pad);
     if (rc) return rc;
-    const int order = mode == 0 ? 0 : 1;
+    const int order = (mode == 0 || c->family != 0) ? 0 : 1;
     MatArgs a = mat_args(c, m, m_pad);
     for (int w0 = 0; w0 < G; w0 += cap) {
         const int nb = std::min(cap, G - w0);
@@ -709,7 +736,7 @@ static int moments_device(gpbo_ctx* c, cudaStream_t s, int mode, const double* t
             scale_rows_kernel<<<nb, 256, 0, s>>>(trow_src + (size_t)w0 * src_stride, src_stride, n, n_pad, order,
                                                  c->pp.as<PairParams>(), c->trow.as<double>());
         });
-        CrossArgs cr{c->trow.as<double>(), n, n_pad, mode == 0 ? 0 : 1};
+        CrossArgs cr{c->trow.as<double>(), n, n_pad, mode == 0 ? 0 : 1, c->family};
         dim3 mgrid((n + NTHR / 32 - 1) / (NTHR / 32), nb);
         launch(c, C_MEAN, s, [&] {
             mean_kernel<<<mgrid, NTHR, 0, s>>>(a, cr, c->alpha.as<double>(), out1 + (size_t)w0 * n, n);

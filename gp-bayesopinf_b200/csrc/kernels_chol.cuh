@@ -55,6 +55,26 @@ struct AsmRbfEval {
     }
 };
 
+// Matern nu = FAM / 2 (FAM = 3 or 5), scikit-learn order (kernels.py:1601-1790: dists = |xi - xj| with x = t / ell,
+// K = dists * sqrt(2 nu), then (1 + K) exp(-K) resp. (1 + K + K^2 / 3) exp(-K)).  Extension: the reference is RBF-only.
+template <int FAM>
+__device__ __forceinline__ double matern_value(double sig2, double dx) {
+    const double K = fabs(dx) * (FAM == 3 ? 1.7320508075688772 : 2.23606797749979);
+    const double e = gpbo_exp(-K);
+    return sig2 * ((FAM == 3) ? (1.0 + K) * e : (1.0 + K + K * K / 3.0) * e);
+}
+template <int FAM>
+struct AsmMatern {
+    double sig2, chi;
+    int m;
+    __device__ __forceinline__ double operator()(int r, int c, double xr, double xc) const {
+        if (r >= m || c >= m) return r == c ? 1.0 : 0.0;
+        if (r == c) return sig2 + chi;
+        return matern_value<FAM>(sig2, xr - xc);
+    }
+};
+
+// ORDER: 0 RBF sklearn order, 1 RBF rbf_eval order, 2 Matern-3/2, 3 Matern-5/2 (both sklearn order, scaled abscissae)
 template <int ORDER>
 struct AsmSelect;
 template <>
@@ -68,6 +88,17 @@ struct AsmSelect<1> {
     static __device__ __forceinline__ type make(const PairParams& q, int m) {
         return {q.sig2, q.chi, 2 * (q.ell * q.ell), 0.5 * q.inv_ell2, m};
     }
+};
+
+template <>
+struct AsmSelect<2> {
+    using type = AsmMatern<3>;
+    static __device__ __forceinline__ type make(const PairParams& q, int m) { return {q.sig2, q.chi, m}; }
+};
+template <>
+struct AsmSelect<3> {
+    using type = AsmMatern<5>;
+    static __device__ __forceinline__ type make(const PairParams& q, int m) { return {q.sig2, q.chi, m}; }
 };
 
 // ---- prep: natural-unit hyper-parameters and scaled abscissae ------------------------------
@@ -439,12 +470,22 @@ struct CrossArgs {
     int nrow;             // valid rows (m')
     int lrow;             // padded rows
     int kind;             // 0: K(t*, t) sklearn order (predict, _gpr.py:446); 1: kappa_zy; 2: K_zy
+    int fam;              // 0 RBF; 3 / 5 Matern (rows and columns are then always t / ell)
 };
 
-__device__ __forceinline__ double cross_element(int kind, const PairParams& q, int r, int c, int nrow, int m,
+__device__ __forceinline__ double cross_element(int kind, int fam, const PairParams& q, int r, int c, int nrow, int m,
                                                 double xr, double xc) {
     if (r >= nrow || c >= m) return 0.0;
     const double d = xr - xc;
+    if (fam != 0) {
+        // Matern: value for kinds 0 / 1, d kappa / d t' for kind 2 (tau = ell d, a^2 = 2 nu / ell^2)
+        if (kind != 2) return fam == 3 ? matern_value<3>(q.sig2, d) : matern_value<5>(q.sig2, d);
+        const double K = fabs(d) * (fam == 3 ? 1.7320508075688772 : 2.23606797749979);
+        const double e = gpbo_exp(-K);
+        const double a2 = (fam == 3 ? 3.0 : 5.0) * q.inv_ell2;
+        const double tau = d * q.ell;
+        return fam == 3 ? -q.sig2 * a2 * tau * e : -q.sig2 * (a2 / 3.0) * tau * (1.0 + K) * e;
+    }
     if (kind == 0) return q.sig2 * gpbo_exp(-0.5 * (d * d));
     const double ell2 = q.ell * q.ell;
     const double kap = q.sig2 * gpbo_exp(-gpbo_div(d * d, 2 * ell2, 0.5 * q.inv_ell2));
@@ -500,7 +541,7 @@ chol_panel_kernel(MatArgs a, int j, double* X, long x_stride, int xT, CrossArgs 
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int r = i * TB + tc.row(mi), c = j * TB + tc.col(ni, e);
-                    const double kv = CROSS ? cross_element(cr.kind, q, r, c, cr.nrow, a.m, xr[mi], xc[ni][e])
+                    const double kv = CROSS ? cross_element(cr.kind, cr.fam, q, r, c, cr.nrow, a.m, xr[mi], xc[ni][e])
                                             : el(r, c, xr[mi], xc[ni][e]);
                     acc.v[mi][ni][e] = kv - acc.v[mi][ni][e];
                 }
@@ -675,6 +716,9 @@ __global__ void __launch_bounds__(NTHR, 1) trtri_row_kernel(MatArgs a, int i, Pr
 //   s1 = sum_ij (a_i a_j - Kinv_ij) sigma^2 R_ij (x_i - x_j)^2
 //   s2 = sum_i  (a_i^2   - Kinv_ii)
 // Off-diagonal tiles are counted twice (symmetry).  part[p][tile][4].
+// FAM: 0 RBF (the reference), 3 / 5 Matern (dK/dlog ell from sklearn kernels.py: 3 D exp(-sqrt(3 D)) resp.
+// 5/3 D (sqrt(5 D) + 1) exp(-sqrt(5 D)), D = squared scaled distance).
+template <int FAM>
 __global__ void __launch_bounds__(NTHR, 1)
 lauum_grad_kernel(MatArgs a, const double* __restrict__ alpha, double* __restrict__ part, int ntiles) {
     extern __shared__ __align__(16) double smem[];
@@ -744,9 +788,18 @@ lauum_grad_kernel(MatArgs a, const double* __restrict__ alpha, double* __restric
                     } else {
                         const double d = xr[mi] - xc[ni][e];
                         const double d2 = d * d;
-                        const double kr = pr.sig2 * gpbo_exp(-0.5 * d2);
+                        double kr, dkl;        // sigma^2 R_ij and dK_ij / dlog(ell)
+                        if (FAM == 0) {
+                            kr = pr.sig2 * gpbo_exp(-0.5 * d2);
+                            dkl = kr * d2;
+                        } else {
+                            const double K = fabs(d) * (FAM == 3 ? 1.7320508075688772 : 2.23606797749979);
+                            const double ex = gpbo_exp(-K);
+                            kr = pr.sig2 * ((FAM == 3) ? (1.0 + K) * ex : (1.0 + K + K * K / 3.0) * ex);
+                            dkl = pr.sig2 * ((FAM == 3) ? 3.0 * d2 * ex : 5.0 / 3.0 * d2 * (K + 1.0) * ex);
+                        }
                         s[0] += wgt * (w * kr);
-                        s[1] += wgt * (w * (kr * d2));
+                        s[1] += wgt * (w * dkl);
                     }
                 }
             }

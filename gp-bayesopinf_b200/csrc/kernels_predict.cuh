@@ -22,7 +22,7 @@ mean_kernel(MatArgs a, CrossArgs cr, const double* __restrict__ alpha, double* _
     const double* tsp = a.ts + (long)p * a.lda;
     const double* al = alpha + (long)p * a.lda;
     double s = 0.0;
-    for (int j = lane; j < a.m; j += 32) s += cross_element(cr.kind, q, row, j, cr.nrow, a.m, xr, tsp[j]) * al[j];
+    for (int j = lane; j < a.m; j += 32) s += cross_element(cr.kind, cr.fam, q, row, j, cr.nrow, a.m, xr, tsp[j]) * al[j];
     s = warp_sum(s);
     if (lane == 0) out[(long)p * out_stride + row] = s;
 }
@@ -97,8 +97,16 @@ schur_kernel(MatArgs a, const double* __restrict__ X, long x_stride, CrossArgs c
                 if (r < n && c < n && c <= r) {
                     const double d = xr[mi] - xc[ni][e];
                     const double d2 = d * d;
-                    const double kap = pr.sig2 * gpbo_exp(-gpbo_div(d2, 2 * ell2, 0.5 * pr.inv_ell2));
-                    const double kzz = gpbo_div((1 - gpbo_div(d2, ell2, pr.inv_ell2)) * kap, ell2, pr.inv_ell2);
+                    double kzz;
+                    if (cr.fam == 0) {
+                        const double kap = pr.sig2 * gpbo_exp(-gpbo_div(d2, 2 * ell2, 0.5 * pr.inv_ell2));
+                        kzz = gpbo_div((1 - gpbo_div(d2, ell2, pr.inv_ell2)) * kap, ell2, pr.inv_ell2);
+                    } else {   // Matern: -kappa''(tau), rows are t' / ell
+                        const double K = fabs(d) * (cr.fam == 3 ? 1.7320508075688772 : 2.23606797749979);
+                        const double ex = gpbo_exp(-K);
+                        const double a2 = (cr.fam == 3 ? 3.0 : 5.0) * pr.inv_ell2;
+                        kzz = cr.fam == 3 ? pr.sig2 * a2 * (1.0 - K) * ex : pr.sig2 * (a2 / 3.0) * (1.0 + K - K * K) * ex;
+                    }
                     const double v = kzz - acc.v[mi][ni][e];
                     Cp[(long)r * n + c] = v;
                     if (r != c) Cp[(long)c * n + r] = v;

@@ -22,7 +22,7 @@ import numpy as np
 
 from . import _lib
 
-__all__ = ["GP_RBFW", "ConvergenceWarning"]
+__all__ = ["GP_RBFW", "GP_MaternW", "ConvergenceWarning"]
 
 
 class ConvergenceWarning(UserWarning):
@@ -83,12 +83,14 @@ class _GPRState:
         self.bounds_log = np.array(bounds_log, dtype=np.float64)
         self.kernel_ = None
         self._ctx_device = None
+        self._twice_nu = 0
 
     def log_marginal_likelihood(self, theta=None, eval_gradient=False):
         """GPU evaluation of sklearn's ``log_marginal_likelihood`` (_gpr.py:541-656)."""
         if theta is None:
             return self.log_marginal_likelihood_value_
         ctx = _lib.default_context(self._ctx_device)
+        ctx.set_kernel_family(self._twice_nu)
         lml, grad, _ = ctx.lml_grad(self.X_train_[:, 0][None, :], self.y_train_[None, :],
                                     np.asarray(theta, dtype=np.float64)[None, :])
         if eval_gradient:
@@ -130,6 +132,13 @@ class GP_RBFW:
         bounds = np.array([constant_bounds, length_scale_bounds, noise_level_bounds], dtype=np.float64)
         self.gpr = _GPRState(np.log(bounds), n_restarts_optimizer)
 
+    _twice_nu = 0          # kernel family of the library calls: 0 = RBF (the reference's kernel)
+
+    def _context(self):
+        ctx = _lib.default_context()
+        ctx.set_kernel_family(self._twice_nu)
+        return ctx
+
     # Properties ----------------------------------------------------------------
     @property
     def nsamples(self):
@@ -169,7 +178,7 @@ class GP_RBFW:
         if not (np.all(np.isfinite(t_training)) and np.all(np.isfinite(np.asarray(training_data, dtype=np.float64)))):
             raise ValueError("Input contains NaN or infinity.")      # sklearn validate_data in GaussianProcessRegressor.fit
         starts = np.vstack([np.zeros((1, 3)), draw_restart_points(self.gpr.bounds_log, self.gpr.n_restarts_optimizer)])
-        ctx = _lib.default_context()
+        ctx = self._context()
         res = ctx.fit(t_training[None, :], training_data[None, :], self.gpr.bounds_log, starts,
                       gp_of=np.zeros(len(starts), dtype=np.int32))
         self._set_fit_result(t_training, training_data, res["theta"], res["fun"], res["status"])
@@ -205,7 +214,7 @@ class GP_RBFW:
     def predict(self, t):
         """(mean, std) of the posterior at ``t`` (gpkernels.py:350-365 -> _gpr.py:444-500)."""
         t = np.asarray(t, dtype=np.float64)
-        ctx = _lib.default_context()
+        ctx = self._context()
         mean, std, _, st = ctx.predict(self.t_training[None, :], self.y[None, :], self.gpr.kernel_.theta[None, :], t)
         if st[0] != 0:
             raise np.linalg.LinAlgError("kernel matrix not positive definite")
@@ -230,7 +239,7 @@ class GP_RBFW:
     def _assemble(self, kind, t1, t2):
         import torch  # tensor hand-off only
 
-        ctx = _lib.default_context()
+        ctx = self._context()
         dev = torch.device("cuda", ctx.device)
         a = torch.as_tensor(np.ascontiguousarray(t1, dtype=np.float64), device=dev)
         b = torch.as_tensor(np.ascontiguousarray(t2, dtype=np.float64), device=dev)
@@ -238,7 +247,7 @@ class GP_RBFW:
         out = torch.empty((a.numel(), b.numel()), dtype=torch.float64, device=dev)
         torch.cuda.synchronize(dev)
         ctx.assemble_device(kind, a.data_ptr(), 0, a.numel(), b.data_ptr(), 0, b.numel(), th.data_ptr(), 1,
-                            out.data_ptr(), 0)
+                            out.data_ptr(), 0, twice_nu=self._twice_nu)
         return out.cpu().numpy()
 
     def __call__(self, t, tprime):
@@ -265,7 +274,7 @@ class GP_RBFW:
     def compute_lstsq_matrices(self, t_est, eta=1e-8):
         """state_estimate, ddt_estimate, ddt_covariance, sqrtW at ``t_est`` (gpkernels.py:612-649, 445-504)."""
         t_est = np.asarray(t_est, dtype=np.float64)
-        ctx = _lib.default_context()
+        ctx = self._context()
         state, ddt, cov, w, st, wst, _ = ctx.lstsq_weights(self.t_training[None, :], self.y[None, :],
                                                            self.gpr.kernel_.theta[None, :], t_est, eta)
         self._set_lstsq_result(t_est, state[0], ddt[0], cov[0], int(st[0]), w[0], int(wst[0]))
@@ -282,3 +291,32 @@ class GP_RBFW:
         if w_status != 0:                                  # gpkernels.py:500-503
             raise ValueError("inverse covariance not positive definite, increase eta")
         self.sqrtW = sqrtW
+
+
+class GP_MaternW(GP_RBFW):
+    """Same interface with a Matern kernel, ``sigma^2 M_nu(|t - t'| / ell) + chi delta(t, t')``, nu in {1.5, 2.5}.
+
+    An extension: the reference has only the RBF kernel.  Semantics follow scikit-learn's
+    ``ConstantKernel * Matern(nu) + WhiteKernel`` (``sklearn/gaussian_process/kernels.py:1601-1790``) for the fit,
+    the LML and ``predict``; ``compute_lstsq_matrices`` uses the analytic derivatives of the Matern kernel
+    (``K_zy = d kappa / d t'``, ``K_zz = d^2 kappa / d t' d t``) in the reference's formulas (``gpkernels.py:445-504``).
+    ``rbf_eval`` returns the Matern kernel value (no noise term), like ``__call__``.
+    """
+
+    def __init__(self, nu=2.5, constant_bounds=(1e-5, 1e5), length_scale_bounds=(1e-5, 1e2),
+                 noise_level_bounds=(1e-16, 1e2), n_restarts_optimizer=50):
+        if nu not in (1.5, 2.5):
+            raise ValueError("GP_MaternW supports nu = 1.5 and nu = 2.5")
+        super().__init__(constant_bounds, length_scale_bounds, noise_level_bounds, n_restarts_optimizer)
+        self.nu = nu
+        self._twice_nu = int(round(2 * nu))
+        self.gpr._twice_nu = self._twice_nu
+
+    def __str__(self):
+        return "\n\t".join([
+            f"Gaussian process with Matern kernel, nu = {self.nu}",
+            r"k(t, t') = \sigma^2 M_\nu(|t - t'| / \ell) + \chi I",
+            rf"\sigma^2 = {self.constant:.4e}",
+            rf"\ell = {self.length_scale:.4e}",
+            rf"\chi = {self.noise_level:.4e}",
+        ])

@@ -21,7 +21,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import _lib, sharding
-from .gpkernels import GP_RBFW, draw_restart_points
+from .gpkernels import GP_MaternW, GP_RBFW, draw_restart_points
 
 __all__ = ["fit_gaussian_processes", "fit_gaussian_processes_multi"]
 
@@ -56,7 +56,7 @@ def _as_time_matrix(time_domain_sampled, num_vars, sample_size):
 
 def fit_gaussian_processes(time_domain_training, time_domain_sampled, snapshots_sampled, gp_regularizer=1e-8, *,
                            constant_bounds=None, length_scale_bounds=None, noise_level_bounds=None,
-                           n_restarts_optimizer=None, verbose=True, group=None, want_sqrtW=True):
+                           n_restarts_optimizer=None, verbose=True, group=None, want_sqrtW=True, kernel="rbf"):
     """Fit one GP per row of ``snapshots_sampled`` and compute its least-squares data.
 
     Parameters follow the reference; ``time_domain_sampled`` may be one (m,) vector (PDE flavour) or a
@@ -66,18 +66,24 @@ def fit_gaussian_processes(time_domain_training, time_domain_sampled, snapshots_
         time_domain_training, [time_domain_sampled], [snapshots_sampled], gp_regularizer,
         constant_bounds=constant_bounds, length_scale_bounds=length_scale_bounds,
         noise_level_bounds=noise_level_bounds, n_restarts_optimizer=n_restarts_optimizer, verbose=verbose,
-        group=group, want_sqrtW=want_sqrtW)
+        group=group, want_sqrtW=want_sqrtW, kernel=kernel)
     return gps[0]
+
+
+_KERNELS = {"rbf": 0, "matern32": 3, "matern52": 5}
 
 
 def fit_gaussian_processes_multi(time_domain_training, time_domains_sampled, snapshots_list, gp_regularizer=1e-8, *,
                                  constant_bounds=None, length_scale_bounds=None, noise_level_bounds=None,
-                                 n_restarts_optimizer=None, verbose=True, group=None, want_sqrtW=True):
+                                 n_restarts_optimizer=None, verbose=True, group=None, want_sqrtW=True, kernel="rbf"):
     """Multi-trajectory form: the loop of ``PDEsMulti/main.py:99-109`` as ONE batch (L trajectories x r modes).
 
     ``time_domains_sampled[l]`` / ``snapshots_list[l]`` are trajectory l's sample times and (r, m) data.
     Returns ``gps[l][i]``.  All trajectories must share the sample count m (they do in the reference).
     """
+    if kernel not in _KERNELS:
+        raise ValueError(f"kernel must be one of {sorted(_KERNELS)}")    # "rbf" is the reference's kernel
+    twice_nu = _KERNELS[kernel]
     cb = _config_value("CONSTANT_VALUE_BOUNDS", constant_bounds)
     lb = _config_value("LENGTH_SCALE_BOUNDS", length_scale_bounds)
     nb = _config_value("NOISE_LEVEL_BOUNDS", noise_level_bounds)
@@ -103,7 +109,7 @@ def fit_gaussian_processes_multi(time_domain_training, time_domains_sampled, sna
         raise ValueError("Input contains NaN or infinity.")          # sklearn validate_data in GaussianProcessRegressor.fit
 
     # 1. restart points, in the reference's order (all ranks draw the same stream)
-    objs = [GP_RBFW(cb, lb, nb, nres) for _ in range(G)]
+    objs = [GP_RBFW(cb, lb, nb, nres) if twice_nu == 0 else GP_MaternW(twice_nu / 2, cb, lb, nb, nres) for _ in range(G)]
     bounds_log = objs[0].gpr.bounds_log
     S = nres + 1
     starts = np.zeros((G, S, 3))
@@ -113,6 +119,7 @@ def fit_gaussian_processes_multi(time_domain_training, time_domains_sampled, sna
 
     # 2. lock-step optimisation of all pairs (sharded over ranks when a process group is given)
     ctx = _lib.default_context()
+    ctx.set_kernel_family(twice_nu)
     res = sharding.fit_pairs(ctx, T, Y, bounds_log, starts.reshape(-1, 3), gp_of, group=group)
     thetas = res["theta"].reshape(G, S, 3)
     funs = res["fun"].reshape(G, S)

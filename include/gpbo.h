@@ -47,6 +47,12 @@ const char* gpbo_last_error(void);
 int gpbo_create(gpbo_ctx** out, int device, size_t max_workspace_bytes);
 int gpbo_destroy(gpbo_ctx* ctx);
 
+/* Kernel family used by every fit / LML / prediction entry point of this handle: 0 = RBF, the reference's
+ * (ConstantKernel * RBF) + WhiteKernel (default); 3 / 5 = Matern nu = 3/2, 5/2 with scikit-learn's Matern semantics
+ * (kernels.py:1601-1790) -- an extension, the reference has no Matern kernel.  The derivative quantities of
+ * gpbo_lstsq_moments* are then the analytic d/dt' and d^2/dt'dt of the Matern kernel. */
+int gpbo_set_kernel_family(gpbo_ctx* ctx, int twice_nu);
+
 /* Number of CUDA kernels this handle has launched so far (for bench accounting). */
 long long gpbo_launch_count(const gpbo_ctx* ctx);
 /* Number of pairs a wave can hold at training size m (derived from the memory limit). */

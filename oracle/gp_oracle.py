@@ -160,6 +160,90 @@ def np_sqrtW(C, eta):
 
 
 # --------------------------------------------------------------------------
+# Matern extension (the reference has no Matern kernel; BASELINE.json's north
+# star names it).  Oracle = scikit-learn's Matern for K / dK, the analytic
+# derivatives of the same kernel for the cross-covariances.
+# --------------------------------------------------------------------------
+def np_matern(t1, t2, sig2, ell, twice_nu, deriv=0):
+    """sigma^2 M_nu((t1 - t2) / ell) for nu = twice_nu / 2 in {3/2, 5/2} (sklearn
+    ``kernels.py:1601-1790``: K = dists * sqrt(2 nu); (1 + K) exp(-K) resp.
+    (1 + K + K^2/3) exp(-K)), or its derivatives w.r.t. the UNSCALED times:
+    deriv=1: d k / d t1;  deriv=2: d^2 k / d t1 d t2 = -k''(tau)."""
+    tau = np.asarray(t1, dtype=np.float64)[:, None] - np.asarray(t2, dtype=np.float64)[None, :]
+    a = np.sqrt(float(twice_nu)) / ell
+    K = a * np.abs(tau)
+    e = np.exp(-K)
+    if twice_nu == 3:
+        if deriv == 0:
+            return sig2 * (1.0 + K) * e
+        if deriv == 1:
+            return -sig2 * a**2 * tau * e
+        return sig2 * a**2 * (1.0 - K) * e
+    if twice_nu == 5:
+        if deriv == 0:
+            return sig2 * (1.0 + K + K**2 / 3.0) * e
+        if deriv == 1:
+            return -sig2 * a**2 / 3.0 * tau * (1.0 + K) * e
+        return sig2 * a**2 / 3.0 * (1.0 + K - K**2) * e
+    raise ValueError("twice_nu must be 3 or 5")
+
+
+def sk_matern_kernel(theta, twice_nu, bounds=None):
+    """scikit-learn's (ConstantKernel * Matern(nu)) + WhiteKernel at log-hyperparameters theta."""
+    from sklearn.gaussian_process.kernels import ConstantKernel, Matern, WhiteKernel
+
+    s2, ell, chi = np.exp(np.asarray(theta, dtype=np.float64))
+    b = [(1e-300, 1e300)] * 3 if bounds is None else [tuple(x) for x in bounds]
+    return (ConstantKernel(s2, constant_value_bounds=b[0]) * Matern(length_scale=ell, nu=twice_nu / 2,
+                                                                    length_scale_bounds=b[1])
+            + WhiteKernel(chi, noise_level_bounds=b[2]))
+
+
+def np_lml_grad_matern(t, y, theta, twice_nu):
+    """LML and gradient exactly as sklearn's regressor computes them (``_gpr.py:583-651``) with the Matern kernel.
+    Returns (lml, grad[3], status)."""
+    y = np.asarray(y, dtype=np.float64)
+    K, dK = sk_matern_kernel(theta, twice_nu)(np.asarray(t, dtype=np.float64)[:, None], eval_gradient=True)
+    try:
+        L = la.cholesky(K, lower=True, check_finite=False)
+    except la.LinAlgError:
+        return -np.inf, np.zeros(3), 1
+    alpha = la.cho_solve((L, True), y, check_finite=False)
+    lml = -0.5 * float(y @ alpha) - float(np.log(np.diag(L)).sum()) - 0.5 * K.shape[0] * LOG_2PI
+    Kinv = la.cho_solve((L, True), np.eye(K.shape[0]), check_finite=False)
+    grad = 0.5 * np.einsum("ij,jik->k", np.outer(alpha, alpha) - Kinv, dK)
+    return lml, grad, 0
+
+
+def np_predict_matern(t, y, theta, t_star, twice_nu):
+    """Posterior mean / std with the Matern kernel (sklearn ``_gpr.py:444-500`` arithmetic)."""
+    sig2, ell, chi = np.exp(np.asarray(theta, dtype=np.float64))
+    K = np_matern(t, t, sig2, ell, twice_nu) + chi * np.eye(len(t))
+    L = la.cholesky(K, lower=True, check_finite=False)
+    alpha = la.cho_solve((L, True), np.asarray(y, dtype=np.float64), check_finite=False)
+    Ks = np_matern(t_star, t, sig2, ell, twice_nu)
+    V = la.solve_triangular(L, Ks.T, lower=True, check_finite=False)
+    var = (sig2 + chi) - np.einsum("ij,ij->j", V, V)
+    var[var < 0] = 0.0
+    return Ks @ alpha, np.sqrt(var), alpha
+
+
+def np_lstsq_moments_matern(t, y, theta, t_est, twice_nu):
+    """The quantities of ``_compute_estimates_and_weights`` (``gpkernels.py:445-493``) with the Matern kernel:
+    state = kappa_zy alpha, ddt = K_zy alpha, C = K_zz - K_zy K_yy^-1 K_zy^T, with K_zy = d kappa / d t',
+    K_zz = d^2 kappa / d t' d t."""
+    sig2, ell, chi = np.exp(np.asarray(theta, dtype=np.float64))
+    K_yy = np_matern(t, t, sig2, ell, twice_nu) + chi * np.eye(len(t))
+    k_zy = np_matern(t_est, t, sig2, ell, twice_nu)
+    K_zy = np_matern(t_est, t, sig2, ell, twice_nu, deriv=1)
+    K_zz = np_matern(t_est, t_est, sig2, ell, twice_nu, deriv=2)
+    cf = la.cho_factor(K_yy, check_finite=True)
+    a = la.cho_solve(cf, np.asarray(y, dtype=np.float64))
+    X = K_zy @ la.cho_solve(cf, K_zy.T)
+    return dict(state_estimate=k_zy @ a, ddt_estimate=K_zy @ a, ddt_covariance=K_zz - 0.5 * (X + X.T))
+
+
+# --------------------------------------------------------------------------
 # Restatement of gpkernels.GP_RBFW on top of scikit-learn (as the reference)
 # --------------------------------------------------------------------------
 class OracleGP:
@@ -169,13 +253,15 @@ class OracleGP:
     NumPy RNG exactly as in the reference (``_gpr.py:251,330``)."""
 
     def __init__(self, constant_bounds, length_scale_bounds, noise_level_bounds,
-                 n_restarts_optimizer):
+                 n_restarts_optimizer, twice_nu=0):
         from sklearn.gaussian_process import GaussianProcessRegressor
-        from sklearn.gaussian_process.kernels import RBF, ConstantKernel, WhiteKernel
+        from sklearn.gaussian_process.kernels import RBF, ConstantKernel, Matern, WhiteKernel
 
+        self.twice_nu = twice_nu      # 0: RBF (the reference); 3 / 5: Matern extension
+        base = (RBF(length_scale_bounds=length_scale_bounds) if twice_nu == 0
+                else Matern(length_scale_bounds=length_scale_bounds, nu=twice_nu / 2))
         kernel = (
-            ConstantKernel(1.0, constant_value_bounds=constant_bounds)
-            * RBF(length_scale_bounds=length_scale_bounds)
+            ConstantKernel(1.0, constant_value_bounds=constant_bounds) * base
         ) + WhiteKernel(noise_level_bounds=noise_level_bounds)
         self.gpr = GaussianProcessRegressor(
             kernel=kernel, n_restarts_optimizer=n_restarts_optimizer, alpha=0

@@ -23,8 +23,11 @@ def load_golden(name):
 REAL_CONFIGS = ("seird_090_090_10_360", "heat_1_20_05_80_5", "euler_006_200_03_400_6", "seird_120_010_05_480")
 
 
-@pytest.fixture(scope="session")
+@pytest.fixture
 def ctx():
+    """Process-wide library context, reset to the reference's RBF kernel family before every test."""
     from gpbo_pkg import pkg
 
-    return pkg.default_context(0)
+    c = pkg.default_context(0)
+    c.set_kernel_family(0)
+    return c

@@ -318,9 +318,27 @@ def test_moments_against_oracle_tiled_sizes(ctx):
         assert rel(std[gi], s0) <= 1e-7
 
 
+def test_moments_many_estimation_points(ctx):
+    """The m' >> m shape of `PDEs/experiments.sh` (m = 200 samples, m' = 3200 regression points), fitted Euler
+    hyper-parameters, per-GP estimation grids."""
+    g = load_golden("euler_006_200_03_400_6")
+    T, Y, th = g["T"][:2], g["Y"][:2], g["theta_opt"][:2]
+    t_est = np.stack([np.linspace(0, 0.06, 3200), np.linspace(0.001, 0.059, 3200)])
+    state, ddt, cov, w, st, wst, _ = ctx.lstsq_weights(T, Y, th, t_est, 1e-8)
+    assert np.all(st == 0) and np.all(wst == 0)
+    for gi in range(2):
+        ref = orc.np_lstsq_moments(T[gi], Y[gi], th[gi], t_est[gi], want_sqrtW=False)
+        assert rel(state[gi], ref["state_estimate"]) <= 1e-9
+        assert rel(ddt[gi], ref["ddt_estimate"]) <= 1e-9
+        assert rel(cov[gi], ref["ddt_covariance"]) <= 1e-8
+    x = np.random.default_rng(0).standard_normal(3200)
+    A = cov[0] + 1e-8 * np.eye(3200)
+    assert np.abs(w[0] @ (A @ (w[0] @ x)) - x).max() <= 1e-4 * np.abs(x).max()
+
+
 # ------------------------------------------------------------------ optimiser
 @pytest.mark.parametrize("name,tol", [("heat_1_20_05_80_5", 1e-8), ("seird_090_090_10_360", 1e-8),
-                                      ("euler_006_200_03_400_6", 1e-8)])
+                                      ("euler_006_200_03_400_6", 1e-8), ("seird_120_010_05_480", 1e-8)])
 def test_fit_reaches_reference_optimum(ctx, name, tol):
     """Same data, bounds and restart points as the reference run -> best LML within 1e-8 relative."""
     g = load_golden(name)
@@ -409,3 +427,79 @@ def test_lstsq_weights_one_call_equals_two(ctx):
     for k in range(3):
         A = c2[k] + 1e-8 * np.eye(260)
         assert np.abs(w2[k] @ A @ w2[k] - np.eye(260)).max() <= 1e-5
+
+
+# ------------------------------------------------------------------ Matern extension (no counterpart in the reference)
+@pytest.mark.parametrize("twice_nu", [3, 5])
+@pytest.mark.parametrize("m", [90, 333, 700])
+def test_matern_lml_grad_against_sklearn(ctx, twice_nu, m):
+    t, y = orc.synthetic_trajectories(2, m, seed=m + twice_nu)
+    thetas = np.log(np.array([[1.0, 0.1, 1e-3], [2.5, 0.05, 1e-2], [0.7, 0.6, 3e-3]]))
+    T = np.tile(t, (2, 1))
+    theta = np.tile(thetas, (2, 1))
+    gp_of = np.repeat(np.arange(2, dtype=np.int32), len(thetas))
+    ctx.set_kernel_family(twice_nu)
+    try:
+        lml, grad, st = ctx.lml_grad(T, y, theta, gp_of)
+    finally:
+        ctx.set_kernel_family(0)
+    for k in range(len(theta)):
+        l0, g0, s0 = orc.np_lml_grad_matern(t, y[gp_of[k]], theta[k], twice_nu)
+        assert st[k] == s0 == 0
+        assert abs(lml[k] - l0) <= 1e-10 * abs(l0), (twice_nu, m, k, lml[k], l0)
+        assert rel(grad[k], g0, max(1.0, np.abs(g0).max())) <= 1e-9, (twice_nu, m, k, grad[k], g0)
+
+
+@pytest.mark.parametrize("twice_nu", [3, 5])
+def test_matern_moments_against_oracle(ctx, twice_nu):
+    t, y = orc.synthetic_trajectories(2, 300, seed=40 + twice_nu)
+    th = np.log(np.array([[2.5, 0.08, 1e-2], [0.7, 0.3, 3e-3]]))
+    t_est = np.linspace(0, 1, 389)
+    T = np.tile(t, (2, 1))
+    ctx.set_kernel_family(twice_nu)
+    try:
+        state, ddt, cov, w, st, wst, _ = ctx.lstsq_weights(T, y, th, t_est, 1e-8)
+        mean, std, alpha, _ = ctx.predict(T, y, th, t_est, want_alpha=True)
+    finally:
+        ctx.set_kernel_family(0)
+    assert np.all(st == 0) and np.all(wst == 0)
+    for gi in range(2):
+        ref = orc.np_lstsq_moments_matern(t, y[gi], th[gi], t_est, twice_nu)
+        assert rel(state[gi], ref["state_estimate"]) <= 1e-10
+        assert rel(ddt[gi], ref["ddt_estimate"]) <= 1e-10
+        assert rel(cov[gi], ref["ddt_covariance"]) <= 1e-9
+        m0, s0, a0 = orc.np_predict_matern(t, y[gi], th[gi], t_est, twice_nu)
+        assert rel(mean[gi], m0) <= 1e-10 and rel(std[gi], s0) <= 1e-7 and rel(alpha[gi], a0) <= 1e-9
+        A = cov[gi] + 1e-8 * np.eye(389)
+        assert np.abs(w[gi] @ A @ w[gi] - np.eye(389)).max() <= 1e-5
+
+
+@pytest.mark.parametrize("nu", [1.5, 2.5])
+def test_matern_fit_reaches_sklearn_optimum(nu):
+    """GP_MaternW.fit against scikit-learn's own GaussianProcessRegressor with the Matern kernel, same restart points
+    (global NumPy RNG, same seed): best LML within 1e-8 relative."""
+    from gpbo_pkg import pkg
+
+    t, y = orc.synthetic_trajectories(1, 80, seed=int(10 * nu))
+    bounds = ((1e-5, 1e5), (1e-5, 1e2), (1e-16, 1e2))
+    np.random.seed(99)
+    ref = orc.OracleGP(*bounds, 12, twice_nu=int(2 * nu)).fit(t, y[0])
+    np.random.seed(99)
+    gp = pkg.GP_MaternW(nu, *bounds, 12).fit(t, y[0])
+    assert abs(gp.gpr.log_marginal_likelihood_value_ - ref.lml) <= 1e-8 * abs(ref.lml)
+    ts = np.linspace(0, 1, 57)
+    mean, std = gp.predict(ts)
+    m0, s0, _ = orc.np_predict_matern(t, y[0], gp.gpr.kernel_.theta, ts, int(2 * nu))
+    assert rel(mean, m0) <= 1e-10 and rel(std, s0) <= 1e-7
+    gp.compute_lstsq_matrices(ts, eta=1e-8)
+    refm = orc.np_lstsq_moments_matern(t, y[0], gp.gpr.kernel_.theta, ts, int(2 * nu))
+    assert rel(gp.ddt_estimate, refm["ddt_estimate"]) <= 1e-10 and rel(gp.ddt_covariance, refm["ddt_covariance"]) <= 1e-9
+    assert "Matern" in str(gp) and rel(gp.rbf_eval(ts, t), orc.np_matern(ts, t, gp.constant, gp.length_scale, int(2 * nu))) <= 1e-13
+    # the batched step keeps working with the extension kernel and leaves RBF objects unaffected
+    gps = pkg.fit_gaussian_processes(ts, t, y, 1e-8, constant_bounds=bounds[0], length_scale_bounds=bounds[1],
+                                     noise_level_bounds=bounds[2], n_restarts_optimizer=3, verbose=False,
+                                     kernel="matern32" if nu == 1.5 else "matern52")
+    assert isinstance(gps[0], pkg.GP_MaternW) and gps[0].sqrtW.shape == (57, 57)
+    rbf = pkg.GP_RBFW(*bounds, 2).fit(t, y[0])
+    l0, g0, _ = orc.np_lml_grad(t, y[0], rbf.gpr.kernel_.theta)
+    assert abs(rbf.gpr.log_marginal_likelihood(rbf.gpr.kernel_.theta) - l0) <= 1e-10 * abs(l0)

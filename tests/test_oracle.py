@@ -118,3 +118,29 @@ def test_reference_import_matches_oracle():
     out = orc.np_lstsq_moments(t, y[0], th, t_est, 1e-8, want_sqrtW=False)
     assert rel(out["ddt_covariance"], gp.ddt_covariance) <= 1e-10
     assert rel(out["ddt_estimate"], gp.ddt_estimate) <= 1e-11
+
+
+# ------------------------------------------------------------------ Matern extension of the oracle
+@pytest.mark.parametrize("twice_nu", [3, 5])
+def test_matern_oracle_formulas(twice_nu):
+    """np_matern against scikit-learn's Matern, its derivatives against central differences."""
+    rng = np.random.default_rng(twice_nu)
+    t1, t2 = np.sort(rng.uniform(0, 1, 40)), np.sort(rng.uniform(0, 1, 31))
+    th = np.log([1.3, 0.2, 1e-3])
+    sk = orc.sk_matern_kernel(th, twice_nu)
+    assert rel(orc.np_matern(t1, t2, 1.3, 0.2, twice_nu), sk(t1[:, None], t2[:, None])) <= 1e-14
+    h = 1e-5
+    k = lambda a, b: orc.np_matern(a, b, 1.3, 0.2, twice_nu)
+    d1 = (k(t1 + h, t2) - k(t1 - h, t2)) / (2 * h)
+    far = np.abs(t1[:, None] - t2[None, :]) > 10 * h
+    assert np.abs(d1 - orc.np_matern(t1, t2, 1.3, 0.2, twice_nu, deriv=1))[far].max() <= 1e-7 * np.abs(d1).max()
+    d2 = (k(t1 + h, t2 + h) - k(t1 + h, t2 - h) - k(t1 - h, t2 + h) + k(t1 - h, t2 - h)) / (4 * h * h)
+    assert np.abs(d2 - orc.np_matern(t1, t2, 1.3, 0.2, twice_nu, deriv=2))[far].max() <= 1e-4 * np.abs(d2).max()
+    # LML / gradient restatement against sklearn's own regressor
+    y = np.sin(7 * t1) + 0.05 * rng.standard_normal(40)
+    gp = orc.OracleGP((1e-5, 1e5), (1e-5, 1e2), (1e-16, 1e2), 0, twice_nu=twice_nu)
+    gp.gpr.optimizer = None
+    gp.fit(t1, y)
+    l_ref, g_ref = gp.lml_grad(th)
+    l, g, st = orc.np_lml_grad_matern(t1, y, th, twice_nu)
+    assert st == 0 and abs(l - l_ref) <= 1e-12 * abs(l_ref) and rel(g, g_ref) <= 1e-10
