@@ -79,6 +79,35 @@ GPBO_HD double gpbo_exp(double x) {
     return res;
 }
 
+// Device fast path for arguments x <= 0 (every kernel-matrix element: -d^2/2, -d^2/(2 ell^2), -sqrt(2 nu) d).
+// Same arithmetic as gpbo_exp, with (i) the constants read as constant-bank operands of the DFMAs (as 64-bit
+// immediates they cost two uniform-register moves each: 14 % of the issue slots of the assembly kernel, which is
+// issue bound), (ii) the flush of results below 2^-1021 done with integer selects instead of a branch.
+// NaN is NOT propagated (the result is 0): the abscissae are validated on the host (the *_host entry points reject
+// non-finite t), hyper-parameters enter through sigma^2 which multiplies every element.
+#if defined(__CUDACC__)
+static __device__ __constant__ double GPBO_EXPC[16] = {
+    6755399441055744.0, 1.4426950408889634, -6.9314718055994529e-01, -2.3190468138462996e-17,
+    2.4994246136424405e-08, 2.763236802746315e-07, 2.7557623140145747e-06, 2.4801486320566664e-05,
+    0.0001984126943145065, 0.001388888895141027, 0.008333333333560176, 0.041666666666492075,
+    0.16666666666666166, 0.5000000000000018, 1.0, 1.0};
+
+__device__ __forceinline__ double gpbo_exp_neg(double x) {
+    const double t = fma(x, GPBO_EXPC[1], GPBO_EXPC[0]);
+    const double k = t - GPBO_EXPC[0];
+    double r = fma(k, GPBO_EXPC[2], x);
+    r = fma(k, GPBO_EXPC[3], r);
+    double p = GPBO_EXPC[4];
+#pragma unroll
+    for (int i = 5; i < 16; ++i) p = fma(p, r, GPBO_EXPC[i]);
+    const int ki = __double2loint(t);
+    const int hi = __double2hiint(p) + (ki << 20);
+    const int lo = __double2loint(p);
+    const bool flush = (unsigned)(__double2hiint(x) & 0x7fffffff) > 0x40862000u;     // |x| > 708 (or NaN / inf)
+    return __hiloint2double(flush ? 0 : hi, flush ? 0 : lo);
+}
+#endif
+
 GPBO_HD double gpbo_div(double a, double b, double rb) {
     const double q = a * rb;
     const double e = fma(-q, b, a);

@@ -40,7 +40,7 @@ struct AsmSklearn {
         if (r >= m || c >= m) return r == c ? 1.0 : 0.0;
         if (r == c) return sig2 + chi;
         const double d = xr - xc;
-        return sig2 * gpbo_exp(-0.5 * (d * d));
+        return sig2 * gpbo_exp_neg(-0.5 * (d * d));
     }
 };
 // rbf_eval order (gpkernels.py:608-609, 639): kappa = sigma^2 exp(-(ti-tj)^2 / (2 ell^2)), + chi on the diagonal.
@@ -51,7 +51,7 @@ struct AsmRbfEval {
         if (r >= m || c >= m) return r == c ? 1.0 : 0.0;
         if (r == c) return sig2 + chi;
         const double d = tr - tcn;
-        return sig2 * gpbo_exp(-gpbo_div(d * d, two_ell2, r_two_ell2));
+        return sig2 * gpbo_exp_neg(-gpbo_div(d * d, two_ell2, r_two_ell2));
     }
 };
 
@@ -60,7 +60,7 @@ struct AsmRbfEval {
 template <int FAM>
 __device__ __forceinline__ double matern_value(double sig2, double dx) {
     const double K = fabs(dx) * (FAM == 3 ? 1.7320508075688772 : 2.23606797749979);
-    const double e = gpbo_exp(-K);
+    const double e = gpbo_exp_neg(-K);
     return sig2 * ((FAM == 3) ? (1.0 + K) * e : (1.0 + K + K * K / 3.0) * e);
 }
 template <int FAM>
@@ -481,14 +481,14 @@ __device__ __forceinline__ double cross_element(int kind, int fam, const PairPar
         // Matern: value for kinds 0 / 1, d kappa / d t' for kind 2 (tau = ell d, a^2 = 2 nu / ell^2)
         if (kind != 2) return fam == 3 ? matern_value<3>(q.sig2, d) : matern_value<5>(q.sig2, d);
         const double K = fabs(d) * (fam == 3 ? 1.7320508075688772 : 2.23606797749979);
-        const double e = gpbo_exp(-K);
+        const double e = gpbo_exp_neg(-K);
         const double a2 = (fam == 3 ? 3.0 : 5.0) * q.inv_ell2;
         const double tau = d * q.ell;
         return fam == 3 ? -q.sig2 * a2 * tau * e : -q.sig2 * (a2 / 3.0) * tau * (1.0 + K) * e;
     }
-    if (kind == 0) return q.sig2 * gpbo_exp(-0.5 * (d * d));
+    if (kind == 0) return q.sig2 * gpbo_exp_neg(-0.5 * (d * d));
     const double ell2 = q.ell * q.ell;
-    const double kap = q.sig2 * gpbo_exp(-gpbo_div(d * d, 2 * ell2, 0.5 * q.inv_ell2));
+    const double kap = q.sig2 * gpbo_exp_neg(-gpbo_div(d * d, 2 * ell2, 0.5 * q.inv_ell2));
     if (kind == 1) return kap;
     return gpbo_div(-d * kap, ell2, q.inv_ell2);     // gpkernels.py:640
 }
@@ -790,11 +790,11 @@ lauum_grad_kernel(MatArgs a, const double* __restrict__ alpha, double* __restric
                         const double d2 = d * d;
                         double kr, dkl;        // sigma^2 R_ij and dK_ij / dlog(ell)
                         if (FAM == 0) {
-                            kr = pr.sig2 * gpbo_exp(-0.5 * d2);
+                            kr = pr.sig2 * gpbo_exp_neg(-0.5 * d2);
                             dkl = kr * d2;
                         } else {
                             const double K = fabs(d) * (FAM == 3 ? 1.7320508075688772 : 2.23606797749979);
-                            const double ex = gpbo_exp(-K);
+                            const double ex = gpbo_exp_neg(-K);
                             kr = pr.sig2 * ((FAM == 3) ? (1.0 + K) * ex : (1.0 + K + K * K / 3.0) * ex);
                             dkl = pr.sig2 * ((FAM == 3) ? 3.0 * d2 * ex : 5.0 / 3.0 * d2 * (K + 1.0) * ex);
                         }
