@@ -158,6 +158,31 @@ def test_full_size_gradient_matches_finite_differences(ctx, m, B):
         assert np.all(np.abs(fd - g[:, i]) <= 2e-3 * scale), (m, i, fd, g[:, i])
 
 
+@pytest.mark.parametrize("m", [1, 2, 3, 17, 128, 129])
+def test_tiny_and_boundary_sizes(ctx, m):
+    """m = 1 ... and the sizes around one 128-tile; duplicate abscissae; extreme length scales."""
+    rng = np.random.default_rng(m)
+    t = np.sort(rng.uniform(0, 1, m))
+    if m >= 3:
+        t[1] = t[0]                                   # duplicate sample time: K is singular without the noise term
+    y = np.sin(5 * t) + 0.1 * rng.standard_normal(m)
+    thetas = np.log(np.array([[1.3, 0.2, 1e-2], [0.5, 1e-4, 1e-1], [2.0, 50.0, 1e-3]]))   # ell tiny / huge
+    lml, grad, st = ctx.lml_grad(t[None], y[None], thetas, np.zeros(3, dtype=np.int32))
+    for k in range(3):
+        l0, g0, s0 = orc.np_lml_grad(t, y, thetas[k])
+        assert st[k] == s0 == 0
+        assert abs(lml[k] - l0) <= 1e-10 * max(1.0, abs(l0)), (m, k, lml[k], l0)
+        assert rel(grad[k], g0, max(1.0, np.abs(g0).max())) <= 1e-8, (m, k, grad[k], g0)
+    t_est = np.linspace(0, 1, 5)
+    state, ddt, cov, w, st2, wst, _ = ctx.lstsq_weights(t[None], y[None], thetas[:1], t_est, 1e-8)
+    ref = orc.np_lstsq_moments(t, y, thetas[0], t_est, want_sqrtW=False)
+    assert st2[0] == 0 and wst[0] == 0
+    assert rel(state[0], ref["state_estimate"]) <= 1e-10 and rel(cov[0], ref["ddt_covariance"]) <= 1e-9
+    mean, std, alpha, _ = ctx.predict(t[None], y[None], thetas[:1], t_est[:1], want_alpha=True)
+    m0, s0 = orc.np_predict(t, y, thetas[0], t_est[:1])
+    assert rel(mean[0], m0, max(1e-300, np.abs(m0).max())) <= 1e-10 and abs(std[0, 0] - s0[0]) <= 1e-7 * max(1.0, s0[0])
+
+
 # ------------------------------------------------------------------ assembly
 @pytest.mark.parametrize("n1,n2", [(90, 90), (257, 33), (400, 200)])
 def test_assemble_kinds(ctx, n1, n2):
