@@ -215,8 +215,9 @@ int plan_split(gpbo_ctx* c, cudaStream_t s, const MatArgs& a, int mode, int idx,
 
 // Factor K(theta) for nb pairs and solve for alpha.  order: 0 sklearn, 1 rbf_eval (RBF only; Matern always uses the
 // scaled sklearn order).
+// solve_alpha = false: only z = L^-1 y is computed (the caller gets alpha from the inverse factor after trtri).
 int factor_wave(gpbo_ctx* c, cudaStream_t s, const MatArgs& a, const double* t_dev, const double* ypad,
-                const double* theta_dev, const int* gpof_dev, int nb, int order) {
+                const double* theta_dev, const int* gpof_dev, int nb, int order, bool solve_alpha = true) {
     const int gen = c->family == 0 ? order : (c->family == 3 ? 2 : 3);     // element generator (AsmSelect index)
     if (c->family != 0) order = 0;
     launch(c, C_PREP, s, [&] {
@@ -245,7 +246,8 @@ int factor_wave(gpbo_ctx* c, cudaStream_t s, const MatArgs& a, const double* t_d
         }
     }
     launch(c, C_TRSV, s, [&] { trsv_fwd_kernel<<<nb, TRSV_THR, 0, s>>>(a, ypad, c->z.as<double>()); });
-    launch(c, C_TRSV, s, [&] { trsv_bwd_kernel<<<nb, TRSV_THR, 0, s>>>(a, c->z.as<double>(), c->alpha.as<double>()); });
+    if (solve_alpha)
+        launch(c, C_TRSV, s, [&] { trsv_bwd_kernel<<<nb, TRSV_THR, 0, s>>>(a, c->z.as<double>(), c->alpha.as<double>()); });
     CUDA_TRY(cudaGetLastError());
     return GPBO_OK;
 }
@@ -254,7 +256,7 @@ int eval_wave(gpbo_ctx* c, cudaStream_t s, const double* t_dev, const double* yp
               const double* theta_dev, const int* gpof_dev, int nb, bool with_grad, double* lml, double* grad,
               int* status) {
     MatArgs a = mat_args(c, m, m_pad);
-    int rc = factor_wave(c, s, a, t_dev, ypad, theta_dev, gpof_dev, nb, 0);
+    int rc = factor_wave(c, s, a, t_dev, ypad, theta_dev, gpof_dev, nb, 0, !with_grad);
     if (rc) return rc;
     const int ntiles = a.T * (a.T + 1) / 2;
     if (with_grad) {
@@ -264,6 +266,9 @@ int eval_wave(gpbo_ctx* c, cudaStream_t s, const double* t_dev, const double* yp
             if (rc) return rc;
             launch(c, C_TRTRI, s, [&] { trtri_row_kernel<<<nb * i, NTHR, TILE_SMEM, s>>>(a, i, pre); });
         }
+        launch(c, C_TRSV, s, [&] {
+            alpha_from_inverse_kernel<<<nb * a.T, NTHR, 0, s>>>(a, c->z.as<double>(), c->alpha.as<double>());
+        });
         launch(c, C_LAUUM, s, [&] {
             if (c->family == 0)
                 lauum_grad_kernel<0><<<nb * ntiles, NTHR, MAIN_SMEM, s>>>(a, c->alpha.as<double>(), c->part.as<double>(), ntiles);

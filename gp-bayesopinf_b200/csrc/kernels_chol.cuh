@@ -663,6 +663,46 @@ __global__ void __launch_bounds__(TRSV_THR, 1) trsv_bwd_kernel(MatArgs a, const 
     }
 }
 
+// alpha = L^-T z = W^T z = U z once the inverse factor U = W^T is available (LML + gradient path, after
+// trtri): unlike the backward substitution this has no sequential dependency over the block rows -- one CTA per
+// (pair, block row I) streams U[I][I+1..T) once (coalesced) -- which matters when few pairs are in flight.
+// alpha_I = DT_I z_I + sum_{k > I} U[I][k] z_k.  Accuracy: O(cond(L) eps) like the substitution (cond(L) = sqrt(cond K)).
+__global__ void __launch_bounds__(NTHR) alpha_from_inverse_kernel(MatArgs a, const double* __restrict__ z,
+                                                                  double* __restrict__ alpha) {
+    const int p = blockIdx.x / a.T, I = blockIdx.x % a.T;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double* Ap = a.A + (long)p * a.mat_stride;
+    const double* zp = z + (long)p * a.lda;
+    const double* DTI = a.DT + ((long)p * a.T + I) * (TB * TB);
+    const int k0 = (I + 1) * TB;
+    for (int rg = 0; rg < 4; ++rg) {                   // 16 rows per warp, four at a time (z loaded once for them)
+        const int r0 = warp * 16 + rg * 4;
+        double sacc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int u = 0; u < TB / 32; ++u) {            // diagonal block: DT_I is upper triangular
+            const int c = lane + 32 * u;
+            const double zc = zp[I * TB + c];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (c >= r0 + q) sacc[q] = fma(DTI[(r0 + q) * TB + c], zc, sacc[q]);
+        }
+#pragma unroll 2
+        for (int k = k0 + 2 * lane; k < a.lda; k += 64) {
+            const double2 zz = *reinterpret_cast<const double2*>(zp + k);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const double2 u2 = *reinterpret_cast<const double2*>(Ap + (long)(I * TB + r0 + q) * a.lda + k);
+                sacc[q] += u2.x * zz.x + u2.y * zz.y;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const double sv = warp_sum(sacc[q]);
+            if (lane == 0) alpha[(long)p * a.lda + I * TB + r0 + q] = sv;
+        }
+    }
+}
+
 // ---- triangular inverse, block row i:  W_ij = -inv(L_ii) sum_{k=j}^{i-1} L_ik W_kj -----------
 // stored transposed: U[j-block rows][i-block cols] = W_ij^T (upper triangle of the pair's buffer).
 __global__ void __launch_bounds__(NTHR, 1) trtri_row_kernel(MatArgs a, int i, PreAcc pre) {
