@@ -215,7 +215,8 @@ int plan_split(gpbo_ctx* c, cudaStream_t s, const MatArgs& a, int mode, int idx,
 
 // Factor K(theta) for nb pairs and solve for alpha.  order: 0 sklearn, 1 rbf_eval (RBF only; Matern always uses the
 // scaled sklearn order).
-// solve_alpha = false: only z = L^-1 y is computed (the caller gets alpha from the inverse factor after trtri).
+// solve_alpha = false: neither z = L^-1 y nor alpha is computed (the caller gets both from the inverse factor after
+// trtri: z_from_inverse_kernel, alpha_from_inverse_kernel).
 int factor_wave(gpbo_ctx* c, cudaStream_t s, const MatArgs& a, const double* t_dev, const double* ypad,
                 const double* theta_dev, const int* gpof_dev, int nb, int order, bool solve_alpha = true) {
     const int gen = c->family == 0 ? order : (c->family == 3 ? 2 : 3);     // element generator (AsmSelect index)
@@ -245,9 +246,10 @@ int factor_wave(gpbo_ctx* c, cudaStream_t s, const MatArgs& a, const double* t_d
             });
         }
     }
-    launch(c, C_TRSV, s, [&] { trsv_fwd_kernel<<<nb, TRSV_THR, 0, s>>>(a, ypad, c->z.as<double>()); });
-    if (solve_alpha)
+    if (solve_alpha) {
+        launch(c, C_TRSV, s, [&] { trsv_fwd_kernel<<<nb, TRSV_THR, 0, s>>>(a, ypad, c->z.as<double>()); });
         launch(c, C_TRSV, s, [&] { trsv_bwd_kernel<<<nb, TRSV_THR, 0, s>>>(a, c->z.as<double>(), c->alpha.as<double>()); });
+    }
     CUDA_TRY(cudaGetLastError());
     return GPBO_OK;
 }
@@ -266,6 +268,7 @@ int eval_wave(gpbo_ctx* c, cudaStream_t s, const double* t_dev, const double* yp
             if (rc) return rc;
             launch(c, C_TRTRI, s, [&] { trtri_row_kernel<<<nb * i, NTHR, TILE_SMEM, s>>>(a, i, pre); });
         }
+        launch(c, C_TRSV, s, [&] { z_from_inverse_kernel<<<nb * a.T, NTHR, 0, s>>>(a, ypad, c->z.as<double>()); });
         launch(c, C_TRSV, s, [&] {
             alpha_from_inverse_kernel<<<nb * a.T, NTHR, 0, s>>>(a, c->z.as<double>(), c->alpha.as<double>());
         });

@@ -663,6 +663,35 @@ __global__ void __launch_bounds__(TRSV_THR, 1) trsv_bwd_kernel(MatArgs a, const 
     }
 }
 
+// z = L^-1 y = W y from the inverse factor (same motivation as alpha_from_inverse_kernel below): one CTA per
+// (pair, block k):  z_k = D_k y_k + sum_{I < k} U[I][k]^T y_I,  U[I][k] = W[k][I]^T stored in the upper triangle.
+// Thread (h, c): column c of the block, rows r = h, h + 2, ... (coalesced 1 KB row segments), four partial sums.
+__global__ void __launch_bounds__(NTHR) z_from_inverse_kernel(MatArgs a, const double* __restrict__ ypad,
+                                                              double* __restrict__ z) {
+    __shared__ double part[NTHR];
+    const int p = blockIdx.x / a.T, kb = blockIdx.x % a.T;
+    const int c = threadIdx.x & (TB - 1), h = threadIdx.x >> 7;
+    const double* Ap = a.A + (long)p * a.mat_stride;
+    const double* yp = ypad + (long)a.pp[p].gp * a.lda;
+    const double* Dk = a.D + ((long)p * a.T + kb) * (TB * TB);
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    const int nrow = kb * TB;
+    const double* col = Ap + kb * TB + c;
+    int r = h;
+    for (; r + 6 < nrow; r += 8) {
+        s0 = fma(col[(long)r * a.lda], yp[r], s0);
+        s1 = fma(col[(long)(r + 2) * a.lda], yp[r + 2], s1);
+        s2 = fma(col[(long)(r + 4) * a.lda], yp[r + 4], s2);
+        s3 = fma(col[(long)(r + 6) * a.lda], yp[r + 6], s3);
+    }
+    for (; r < nrow; r += 2) s0 = fma(col[(long)r * a.lda], yp[r], s0);
+    // diagonal block: z_k[c] += sum_{q <= c} D_k[c][q] y_k[q]  (row c of D_k; half of the q range per h)
+    for (int q = h; q <= c; q += 2) s1 = fma(Dk[c * TB + q], yp[kb * TB + q], s1);
+    part[threadIdx.x] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (h == 0) z[(long)p * a.lda + kb * TB + c] = part[c] + part[TB + c];
+}
+
 // alpha = L^-T z = W^T z = U z once the inverse factor U = W^T is available (LML + gradient path, after
 // trtri): unlike the backward substitution this has no sequential dependency over the block rows -- one CTA per
 // (pair, block row I) streams U[I][I+1..T) once (coalesced) -- which matters when few pairs are in flight.
