@@ -29,6 +29,13 @@ class FakeEngine:
         cov = np.einsum("g,i,j->gij", theta[:, 1], t_est, t_est) if want_cov else None
         return state, ddt, cov, np.zeros(G, np.int32)
 
+    def lstsq_weights(self, T, Y, theta, t_est, eta):
+        state, ddt, cov, st = self.lstsq_moments(T, Y, theta, t_est)
+        n = t_est.shape[-1]
+        w = cov + eta * np.eye(n)[None]
+        G = T.shape[0]
+        return state, ddt, cov, w, st, (np.arange(G) % 2).astype(np.int32), np.full(G, 9, np.int32)
+
     def predict(self, T, Y, theta, t_star, want_alpha=False):
         G = T.shape[0]
         alpha = Y * theta[:, 2:3]
@@ -60,6 +67,11 @@ def _worker(rank, world, port, q):
     theta_opt = res["theta"].reshape(G, -1, 3)[np.arange(G), funs.argmin(1)]
     mom = pkg.sharding.moments(eng, T, Y, theta_opt, np.linspace(0, 1, 6), group=True)
     owned = [g for g in range(G) if mom["cov"][g] is not None]
+    # with eta: covariance AND sqrtW stay with the owner, computed by one lstsq_weights call per rank
+    momw = pkg.sharding.moments(eng, T, Y, theta_opt, np.linspace(0, 1, 6), group=True, eta=0.5)
+    owned_w = [g for g in range(G) if momw["sqrtW"][g] is not None]
+    assert owned_w == owned and all(np.array_equal(momw["sqrtW"][g], momw["cov"][g] + 0.5 * np.eye(6)) for g in owned)
+    assert np.array_equal(momw["state"], mom["state"]) and np.array_equal(momw["alpha"], mom["alpha"])
     q.put((rank, res["theta"], res["fun"], res["status"], mom["alpha"], mom["state"], mom["ddt"], owned))
     dist.barrier()
     dist.destroy_process_group()
