@@ -25,6 +25,7 @@ EXPORTS = (
     "gpbo_predict_host", "gpbo_lstsq_moments_host", "gpbo_lstsq_moments", "gpbo_profile_enable",
     "gpbo_profile_get", "gpbo_bench_dmma_peak", "gpbo_lbfgsb_minimize", "gpbo_sqrtw", "gpbo_sqrtw_host",
     "gpbo_lstsq_weights_host", "gpbo_assemble_matern", "gpbo_set_kernel_family",
+    "gpbo_weighted_products_host",
 )
 
 
@@ -72,6 +73,7 @@ def load():
     lib.gpbo_sqrtw_host.argtypes = [vp, dp, C.c_int, C.c_int, C.c_double, dp, ip, ip]
     lib.gpbo_lstsq_weights_host.argtypes = [vp, dp, dp, C.c_int, C.c_int, dp, dp, C.c_long, C.c_int, C.c_double, dp, dp,
                                             dp, dp, ip, ip, ip]
+    lib.gpbo_weighted_products_host.argtypes = [vp, dp, C.c_int, C.c_int, dp, C.c_int, dp, dp, dp]
     lib.gpbo_profile_enable.argtypes = [vp, C.c_int]
     lib.gpbo_profile_get.argtypes = [vp, dp, C.POINTER(C.c_longlong)]
     lib.gpbo_bench_dmma_peak.argtypes = [vp, C.c_int, dp, dp]
@@ -256,6 +258,25 @@ class Context:
                                                  float(eta), _dp(state), _dp(ddt), _dp(cov), _dp(w), _ip(st), _ip(wst),
                                                  _ip(wit)), "gpbo_lstsq_weights_host")
         return state, ddt, cov, w, st, wst, wit
+
+    def weighted_products(self, lhs, rhs, sqrtW=None):
+        """(sqrtW[g] @ lhs, sqrtW[g] @ rhs[g]) for all g (wlstsq.py:183-188).  sqrtW=None: use the weight matrices
+        resident on the device since the last lstsq_weights / sqrtw call (same G, n).  -> (G, n, d), (G, n)."""
+        lhs = _f64(lhs)
+        rhs = _f64(np.atleast_2d(rhs))
+        G, n = rhs.shape
+        if lhs.ndim != 2 or lhs.shape[0] != n:
+            raise ValueError(f"expected lhs.shape == ({n}, d)")
+        d = lhs.shape[1]
+        w = None
+        if sqrtW is not None:
+            w = _f64(sqrtW)
+            if w.shape != (G, n, n):
+                raise ValueError(f"expected sqrtW.shape == ({G}, {n}, {n})")
+        out_lhs, out_rhs = np.empty((G, n, d)), np.empty((G, n))
+        _check(self._lib.gpbo_weighted_products_host(self._h, _dp(w), G, n, _dp(lhs), d, _dp(rhs), _dp(out_lhs),
+                                                     _dp(out_rhs)), "gpbo_weighted_products_host")
+        return out_lhs, out_rhs
 
     # -- device-pointer entry points (torch tensors are only address carriers) ------------
     def assemble_device(self, kind, t1_ptr, t1_stride, n1, t2_ptr, t2_stride, n2, theta_ptr, B, out_ptr, stream=0,

@@ -67,6 +67,8 @@ struct gpbo_ctx {
     DevBuf X, trow, tsrc, out1, out2, cov_dev;
     // sqrtW (Newton-Schulz)
     DevBuf nsY, nsZ, nsT, nsTT, nsYn, nsZn, nsPart, nsNorm, nsResid, w_dev;
+    int w_G = 0, w_n = 0;            // shape of the sqrtW stack currently resident in w_dev
+    DevBuf wp_lhs, wp_rhs, wp_olhs, wp_orhs;
     // split-K partial tiles (small batches)
     DevBuf pre;
     // pinned staging for the optimiser rounds
@@ -442,7 +444,7 @@ int gpbo_destroy(gpbo_ctx* c) {
                       &c->t_dev, &c->y_dev, &c->ypad, &c->theta_dev, &c->gpof_dev, &c->lml_dev, &c->grad_dev, &c->st_dev,
                       &c->X, &c->trow, &c->tsrc, &c->out1, &c->out2, &c->cov_dev,
                       &c->nsY, &c->nsZ, &c->nsT, &c->nsTT, &c->nsYn, &c->nsZn, &c->nsPart, &c->nsNorm, &c->nsResid, &c->w_dev,
-                      &c->pre};
+                      &c->pre, &c->wp_lhs, &c->wp_rhs, &c->wp_olhs, &c->wp_orhs};
     for (DevBuf* b : bufs) b->release();
     for (auto& r : c->recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     if (c->h_theta) cudaFreeHost(c->h_theta);
@@ -821,6 +823,7 @@ static int moments_host(gpbo_ctx* c, int mode, const double* t, const double* y,
         CUDA_TRY(c->w_dev.ensure((size_t)G * n * n * 8));
         rc = sqrtw_device(c, s, c->cov_dev.as<double>(), G, n, eta, c->w_dev.as<double>(), w_status, w_iters);
         if (rc) return rc;
+        c->w_G = G; c->w_n = n;
         CUDA_TRY(cudaMemcpyAsync(sqrtw, c->w_dev.p, (size_t)G * n * n * 8, cudaMemcpyDeviceToHost, s));
     }
     CUDA_TRY(cudaMemcpyAsync(o1, c->out1.p, (size_t)G * n * 8, cudaMemcpyDeviceToHost, s));
@@ -868,7 +871,40 @@ int gpbo_sqrtw_host(gpbo_ctx* c, const double* cov, int G, int n, double eta, do
     CUDA_TRY(cudaMemcpyAsync(c->cov_dev.p, cov, bytes, cudaMemcpyHostToDevice, s));
     int rc = sqrtw_device(c, s, c->cov_dev.as<double>(), G, n, eta, c->w_dev.as<double>(), status, iters);
     if (rc) return rc;
+    c->w_G = G; c->w_n = n;
     CUDA_TRY(cudaMemcpyAsync(sqrtw, c->w_dev.p, bytes, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return GPBO_OK;
+}
+
+int gpbo_weighted_products_host(gpbo_ctx* c, const double* sqrtw, int G, int n, const double* lhs, int d,
+                                const double* rhs, double* out_lhs, double* out_rhs) {
+    if (!c || !lhs || !rhs || !out_lhs || !out_rhs || G <= 0 || n <= 0 || d <= 0)
+        return fail(GPBO_EINVAL, "weighted_products_host: bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    if (sqrtw) {
+        CUDA_TRY(c->w_dev.ensure((size_t)G * n * n * 8));
+        CUDA_TRY(cudaMemcpyAsync(c->w_dev.p, sqrtw, (size_t)G * n * n * 8, cudaMemcpyHostToDevice, s));
+        c->w_G = G; c->w_n = n;
+    } else if (c->w_G != G || c->w_n != n || !c->w_dev.p) {
+        return fail(GPBO_EINVAL, "weighted_products_host: sqrtw is NULL but the resident weight stack has another shape "
+                                 "(call gpbo_lstsq_weights_host / gpbo_sqrtw_host for the same G, n first)");
+    }
+    CUDA_TRY(c->wp_lhs.ensure((size_t)n * d * 8));
+    CUDA_TRY(c->wp_rhs.ensure((size_t)G * n * 8));
+    CUDA_TRY(c->wp_olhs.ensure((size_t)G * n * d * 8));
+    CUDA_TRY(c->wp_orhs.ensure((size_t)G * n * 8));
+    CUDA_TRY(cudaMemcpyAsync(c->wp_lhs.p, lhs, (size_t)n * d * 8, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(c->wp_rhs.p, rhs, (size_t)G * n * 8, cudaMemcpyHostToDevice, s));
+    launch(c, C_SQRTW, s, [&] {
+        weighted_products_kernel<<<dim3((n + NTHR / 32 - 1) / (NTHR / 32), G), NTHR, 0, s>>>(
+            c->w_dev.as<double>(), n, c->wp_lhs.as<double>(), d, c->wp_rhs.as<double>(), c->wp_olhs.as<double>(),
+            c->wp_orhs.as<double>());
+    });
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out_lhs, c->wp_olhs.p, (size_t)G * n * d * 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(out_rhs, c->wp_orhs.p, (size_t)G * n * 8, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     return GPBO_OK;
 }

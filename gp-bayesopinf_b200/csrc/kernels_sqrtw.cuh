@@ -169,4 +169,44 @@ __global__ void __launch_bounds__(NTHR) ns_out_kernel(NsArgs a, const unsigned l
     for (int c = threadIdx.x; c < a.n; c += NTHR) o[c] = Zr[c] * f;
 }
 
+// ---- weighted least-squares products (codebase/wlstsq.py:183-188) -------------------------------
+// For every GP g:  out_lhs[g] = sqrtW[g] @ lhs  (n x d, lhs shared by all GPs)  and  out_rhs[g] = sqrtW[g] @ rhs[g].
+// HBM bound on the n x n weight matrices, which stay in device memory: one warp per output row streams the row of
+// sqrtW once per chunk of WP_DC columns of lhs (the row stays in L1), lanes across k.
+constexpr int WP_DC = 8;
+
+__global__ void __launch_bounds__(NTHR)
+weighted_products_kernel(const double* __restrict__ W, int n, const double* __restrict__ lhs, int d,
+                         const double* __restrict__ rhs, double* __restrict__ out_lhs, double* __restrict__ out_rhs) {
+    const int g = blockIdx.y;
+    const int r = blockIdx.x * (NTHR / 32) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= n) return;
+    const double* Wr = W + ((long)g * n + r) * n;
+    {
+        const double* zg = rhs + (long)g * n;
+        double s = 0.0;
+        for (int k = lane; k < n; k += 32) s = fma(Wr[k], zg[k], s);
+        s = warp_sum(s);
+        if (lane == 0) out_rhs[(long)g * n + r] = s;
+    }
+    for (int c0 = 0; c0 < d; c0 += WP_DC) {
+        double acc[WP_DC];
+#pragma unroll
+        for (int q = 0; q < WP_DC; ++q) acc[q] = 0.0;
+        for (int k = lane; k < n; k += 32) {
+            const double w = Wr[k];
+            const double* Dk = lhs + (long)k * d + c0;
+#pragma unroll
+            for (int q = 0; q < WP_DC; ++q)
+                if (c0 + q < d) acc[q] = fma(w, Dk[q], acc[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < WP_DC; ++q) {
+            const double s = warp_sum(acc[q]);
+            if (lane == 0 && c0 + q < d) out_lhs[((long)g * n + r) * d + c0 + q] = s;
+        }
+    }
+}
+
 }  // namespace gpbo

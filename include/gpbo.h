@@ -144,6 +144,15 @@ int gpbo_lstsq_weights_host(gpbo_ctx* ctx, const double* t, const double* y, int
                             const double* t_est, long test_stride, int n_est, double eta, double* state, double* ddt,
                             double* cov, double* sqrtw, int* status, int* w_status, int* w_iters);
 
+/* Products of the weighted least squares of step 3: for every GP g, out_lhs[g] = sqrtW[g] @ lhs and
+ * out_rhs[g] = sqrtW[g] @ rhs[g].  Replaces `self.weights[i] @ lhs, self.weights[i] @ rhs[i]` of
+ * WeightedLSTSQSolver.fit (codebase/wlstsq.py:183-188).  All pointers HOST.  sqrtw: [G][n][n], or NULL to use the
+ * weight matrices still resident in HBM from the last gpbo_lstsq_weights_host / gpbo_sqrtw_host call of this handle
+ * (same G and n) -- they then never travel to the host for this step.  lhs: [n][d] (shared data matrix D),
+ * rhs: [G][n]; outputs out_lhs [G][n][d], out_rhs [G][n]. */
+int gpbo_weighted_products_host(gpbo_ctx* ctx, const double* sqrtw, int G, int n, const double* lhs, int d,
+                                const double* rhs, double* out_lhs, double* out_rhs);
+
 /* Per-kernel-class device timing (CUDA events on the launching stream), for bench.py's roofline.
  * Classes: 0 prep 1 chol_diag 2 chol_panel 3 trsv 4 trtri 5 lauum_grad 6 finalize 7 cross_panel
  *          8 schur 9 mean_std 10 assemble 11 sqrtw.  `ms` and `launches` are arrays of GPBO_NCLASS entries,

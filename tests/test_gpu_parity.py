@@ -533,3 +533,25 @@ def test_matern_fit_reaches_sklearn_optimum(nu):
     rbf = pkg.GP_RBFW(*bounds, 2).fit(t, y[0])
     l0, g0, _ = orc.np_lml_grad(t, y[0], rbf.gpr.kernel_.theta)
     assert abs(rbf.gpr.log_marginal_likelihood(rbf.gpr.kernel_.theta) - l0) <= 1e-10 * abs(l0)
+
+
+def test_weighted_products(ctx):
+    """sqrtW_i @ D and sqrtW_i @ z_i of WeightedLSTSQSolver.fit (wlstsq.py:183-188), with the weights passed from the
+    host and with the weights left resident on the device by lstsq_weights."""
+    t, y = orc.synthetic_trajectories(3, 150, seed=21)
+    T = np.tile(t, (3, 1))
+    theta = np.log(np.array([[1.5, 0.05, 1e-2], [0.8, 0.1, 3e-3], [2.0, 0.2, 1e-3]]))
+    t_est = np.linspace(0, 1, 203)
+    state, ddt, cov, w, st, wst, _ = ctx.lstsq_weights(T, y, theta, t_est, 1e-6)
+    rng = np.random.default_rng(0)
+    D = rng.standard_normal((203, 27))                      # d not a multiple of the column chunk
+    ol, orr = ctx.weighted_products(D, ddt)                 # resident weights
+    for g in range(3):
+        # summation order differs from BLAS: compare against the rounding scale |W| |x| (sqrtW whitens a smooth
+        # ddt estimate, so the product itself is small by cancellation)
+        assert np.all(np.abs(ol[g] - w[g] @ D) <= 1e-14 * (np.abs(w[g]) @ np.abs(D)))
+        assert np.all(np.abs(orr[g] - w[g] @ ddt[g]) <= 1e-14 * (np.abs(w[g]) @ np.abs(ddt[g])))
+    ol2, or2 = ctx.weighted_products(D[:, :1], ddt, sqrtW=w)
+    assert np.array_equal(ol2[:, :, 0], ol[:, :, 0]) and np.array_equal(or2, orr)
+    with pytest.raises(Exception, match="another shape"):
+        ctx.weighted_products(D[:100], ddt[:, :100])
