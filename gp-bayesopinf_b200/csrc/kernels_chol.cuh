@@ -187,15 +187,28 @@ __device__ __forceinline__ bool chol32_block(double* P, int o, double* dinv, dou
     return bad;
 }
 
-__device__ __forceinline__ bool potf2_trtri_smem(double* P, double* scratch, double* dinv, double* logsum_out) {
+// nv = number of valid (non-padding) rows of the block: rows >= nv are identity rows (the reference's sizes
+// m = 10 ... 200 leave most of a 128-tile as padding), so only the first ceil(nv / 32) panels are factored and
+// inverted; the identity part gets L = W = I directly.
+__device__ __forceinline__ bool potf2_trtri_smem(double* P, double* scratch, double* dinv, double* logsum_out, int nv) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     bool bad = false;
     double* rsv = scratch;
+    const int nvb = (nv + PB - 1) / PB;          // panels that hold valid rows (1..4)
+    const int nact = nvb * PB;                   // rows / columns that take part in the factorisation
     __syncthreads();   // P was just filled by all threads
-    for (int kb = 0; kb < TB / PB; ++kb) {
+    if (nact < TB) {
+        // identity part: 1 / L_ii = 1, and W[r][c] = 0 for r >= nact, c < r (stored transposed at P[c][r])
+        for (int q = tid; q < TB * (TB - nact); q += NTHR) {
+            const int c = q / (TB - nact), r = nact + q % (TB - nact);
+            if (c < r) P[c * LDP + r] = 0.0;
+        }
+        if (tid >= nact && tid < TB) dinv[tid] = 1.0;
+    }
+    for (int kb = 0; kb < nvb; ++kb) {
         const int o = kb * PB;
         bad |= chol32_block(P, o, dinv, rsv);
-        const int R0 = o + PB, n = TB - R0;
+        const int R0 = o + PB, n = nact - R0;
         if (n <= 0) break;
         // (2) panel by forward substitution, one thread per row:  X L_kk^T = A  (row in registers, L_kk broadcast)
         if (tid < n) {
@@ -256,7 +269,7 @@ __device__ __forceinline__ bool potf2_trtri_smem(double* P, double* scratch, dou
     // inverses of the four 32x32 diagonal blocks, all at once: 64 threads per block, 2 lanes per column jc,
     // forward substitution over the rows; W is written transposed into the strict upper part of P, where the
     // column under construction is contiguous.
-    {
+    if ((tid >> 6) < nvb) {                            // whole warps: 64 threads per diagonal block
         const int o = (tid >> 6) * PB, jc = (tid & 63) >> 1, h = tid & 1;
         double* Wc = P + (o + jc) * LDP + o;           // Wc[k] = W[k][jc], k > jc
         const double wjj = dinv[o + jc];
@@ -281,7 +294,7 @@ __device__ __forceinline__ bool potf2_trtri_smem(double* P, double* scratch, dou
     __syncthreads();
     // off-diagonal blocks of W = inv(L), block row bi; W stored transposed in the strict upper part of P
     double* Gs = scratch;
-    for (int bi = 1; bi < TB / PB; ++bi) {
+    for (int bi = 1; bi < nvb; ++bi) {
         const int oi = bi * PB, ncol = oi;
         const int r = oi + lane;
         const double* Lr = P + r * LDP;
@@ -445,7 +458,7 @@ __global__ void __launch_bounds__(NTHR, 1) chol_diag_kernel(MatArgs a, int j, Pr
                         P[r * LDP + c] = el(j * TB + r, j * TB + c, xr[mi], xc[ni][e]) - acc.v[mi][ni][e];
                 }
     }
-    const bool bad = potf2_trtri_smem(P, scratch, dinv, &logsum);
+    const bool bad = potf2_trtri_smem(P, scratch, dinv, &logsum, min(TB, a.m - j * TB));
 
     // write L_jj (lower), D_j = inv(L_jj) and DT_j = D_j^T
     double* Lout = Ap + (long)j * TB * a.lda + j * TB;
