@@ -2,6 +2,7 @@
 // (GP x start) batch, the lock-step multi-start optimiser driver, and the posterior-moment path.
 #include "../../include/gpbo.h"
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -556,7 +557,17 @@ int gpbo_lml_grad(gpbo_ctx* c, const double* t, const double* y, int G, int m, c
     return lml_grad_device(c, static_cast<cudaStream_t>(stream), t, y, G, m, theta, gp_of, B, lml, grad, status);
 }
 
+static bool all_finite(const double* v, size_t n) {
+    for (size_t i = 0; i < n; ++i)
+        if (!std::isfinite(v[i])) return false;
+    return true;
+}
+
+// Host inputs are validated like scikit-learn validates X and y (GaussianProcessRegressor.fit -> validate_data):
+// the kernels' exp fast path maps a NaN abscissa to a finite element instead of propagating it.
 static int upload_problem(gpbo_ctx* c, cudaStream_t s, const double* t, const double* y, int G, int m) {
+    if (!all_finite(t, (size_t)G * m) || !all_finite(y, (size_t)G * m))
+        return fail(GPBO_EINVAL, "input contains NaN or infinity (t or y)");
     CUDA_TRY(c->t_dev.ensure((size_t)G * m * 8));
     CUDA_TRY(c->y_dev.ensure((size_t)G * m * 8));
     CUDA_TRY(cudaMemcpyAsync(c->t_dev.p, t, (size_t)G * m * 8, cudaMemcpyHostToDevice, s));
@@ -806,6 +817,7 @@ static int moments_host(gpbo_ctx* c, int mode, const double* t, const double* y,
     CUDA_TRY(c->theta_dev.ensure((size_t)G * 24));
     CUDA_TRY(cudaMemcpyAsync(c->theta_dev.p, theta, (size_t)G * 24, cudaMemcpyHostToDevice, s));
     const size_t npts = pts_stride == 0 ? (size_t)n : (size_t)G * pts_stride;
+    if (!all_finite(pts, npts)) return fail(GPBO_EINVAL, "evaluation points contain NaN or infinity");
     CUDA_TRY(c->tsrc.ensure(npts * 8));
     CUDA_TRY(cudaMemcpyAsync(c->tsrc.p, pts, npts * 8, cudaMemcpyHostToDevice, s));
     CUDA_TRY(c->out1.ensure((size_t)G * n * 8));

@@ -11,7 +11,8 @@
  *    sklearn's `kernel_.theta` for (ConstantKernel * RBF) + WhiteKernel;
  *  - a "pair" is one (GP, theta) combination; `gp_of[b]` selects which GP's (t, y) pair b uses
  *    (NULL: pair b uses GP b); all GPs of a call share the training size m;
- *  - functions with the suffix `_host` take HOST pointers and perform the H2D/D2H copies themselves;
+ *  - functions with the suffix `_host` take HOST pointers and perform the H2D/D2H copies themselves; they reject
+ *    non-finite t / y / evaluation points with GPBO_EINVAL (scikit-learn validates X and y the same way);
  *    the others take DEVICE pointers and enqueue on `stream` (a cudaStream_t, NULL = default stream)
  *    and return after the work has been enqueued AND completed (they synchronise the stream);
  *  - every function returns 0 on success or a negative GPBO_E* code; `gpbo_last_error()` describes

@@ -122,6 +122,20 @@ def test_error_conventions(pkg):
                                    n_restarts_optimizer=1)        # step2_fitgps.py:87-91
 
 
+def test_non_finite_inputs_are_rejected(pkg, ctx):
+    t, y = orc.synthetic_trajectories(1, 20, seed=1)
+    bad = y[0].copy()
+    bad[3] = np.nan
+    with pytest.raises(ValueError, match="NaN"):
+        pkg.GP_RBFW(*BOUNDS, 1).fit(t, bad)                      # Python layer (sklearn's validate_data message)
+    with pytest.raises(pkg.GpboError, match="NaN or infinity"):
+        ctx.lml_grad(t[None], bad[None], np.zeros((1, 3)))       # C ABI
+    tb = t.copy()
+    tb[0] = np.inf
+    with pytest.raises(pkg.GpboError, match="NaN or infinity"):
+        ctx.predict(tb[None], y, np.zeros((1, 3)), t[:3])
+
+
 @pytest.mark.parametrize("flavour", ["shared_t", "per_variable_t"])
 def test_fit_gaussian_processes_batched(pkg, flavour, monkeypatch, capsys):
     """Batched step2 against the reference's golden run of the Heat config (restart points replayed)."""
