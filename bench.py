@@ -367,11 +367,12 @@ def assembly_roofline(ctx, dev, n=8192, B=8):
 
 
 def fit_reference_configs(ctx):
-    """Full step2 fit (all 101 starts per GP, the reference's own start points) + posterior moments on four of the
+    """Full step2 fit (all 101 starts per GP, the reference's own start points) + posterior moments on five of the
     reference's experiment configurations (tests/golden/*.npz), with the reference's CPU wall time recorded when the
     fixtures were generated (8-core build container) beside it."""
     out = {}
-    for name in ("seird_090_090_10_360", "seird_120_010_05_480", "heat_1_20_05_80_5", "euler_006_200_03_400_6"):
+    for name in ("seird_090_090_10_360", "seird_120_010_05_480", "heat_1_20_05_80_5", "euler_006_200_03_400_6",
+                 "euler_006_050_01_400_6"):
         g = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"), allow_pickle=False)
         T, Y, t_est = g["T"], g["Y"], g["t_est"]
         G = T.shape[0]

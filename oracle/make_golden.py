@@ -194,9 +194,9 @@ def run_reference(data, n_restarts, n_cov=2, label=""):
     return {k: np.array(v) for k, v in out.items()}
 
 
-def make_config(name, data_fn, n_restarts=100):
+def make_config(name, data_fn, n_restarts=100, n_cov=2):
     data = data_fn()
-    res = run_reference(data, n_restarts, label=name)
+    res = run_reference(data, n_restarts, n_cov=n_cov, label=name)
     v = versions()
     np.savez_compressed(
         os.path.join(GOLDEN_DIR, f"{name}.npz"),
@@ -250,6 +250,8 @@ ALL = dict(
     euler=lambda: make_config("euler_006_200_03_400_6", data_euler),
     # sparse-data line of ODEs/experiments.sh (`main.py 120 010 .05 480`): only 10 samples per state
     seird_sparse=lambda: make_config("seird_120_010_05_480", lambda: data_seird(10, 0.05, 480, 120)),
+    # sparse-data line of PDEs/experiments.sh (`main.py 0.06 50 .01 0400 6`): 50 samples, 1 % noise
+    euler_sparse=lambda: make_config("euler_006_050_01_400_6", lambda: data_euler(50, 0.01, 400, 6, 0.06), n_cov=1),
 )
 
 if __name__ == "__main__":

@@ -20,7 +20,8 @@ def load_golden(name):
     return np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
 
 
-REAL_CONFIGS = ("seird_090_090_10_360", "heat_1_20_05_80_5", "euler_006_200_03_400_6", "seird_120_010_05_480")
+REAL_CONFIGS = ("seird_090_090_10_360", "heat_1_20_05_80_5", "euler_006_200_03_400_6", "seird_120_010_05_480",
+                "euler_006_050_01_400_6")
 
 
 @pytest.fixture

@@ -368,7 +368,8 @@ def test_moments_many_estimation_points(ctx):
 
 # ------------------------------------------------------------------ optimiser
 @pytest.mark.parametrize("name,tol", [("heat_1_20_05_80_5", 1e-8), ("seird_090_090_10_360", 1e-8),
-                                      ("euler_006_200_03_400_6", 1e-8), ("seird_120_010_05_480", 1e-8)])
+                                      ("euler_006_200_03_400_6", 1e-8), ("seird_120_010_05_480", 1e-8),
+                                      ("euler_006_050_01_400_6", 1e-8)])
 def test_fit_reaches_reference_optimum(ctx, name, tol):
     """Same data, bounds and restart points as the reference run -> best LML within 1e-8 relative."""
     g = load_golden(name)
