@@ -67,3 +67,20 @@ def test_product_never_imports_the_oracle_or_a_cpu_solver():
             if fn.endswith(".py"):
                 src = open(os.path.join(dirpath, fn)).read()
                 assert not bad.search(src), fn
+
+
+def test_header_is_valid_c_and_cxx(tmp_path):
+    """include/gpbo.h must be consumable by a plain C compiler (the ABI has no C++ or torch types)."""
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None:
+        pytest.skip("needs gcc")
+    hdr = os.path.join(ROOT, "include", "gpbo.h")
+    c = tmp_path / "t.c"
+    c.write_text('#include "gpbo.h"\nint main(void) { gpbo_ctx* c = 0; return gpbo_destroy(c) + (GPBO_NCLASS > 0 ? 0 : 1); }\n')
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-I", os.path.dirname(hdr), str(c)],
+                   check=True)
+    cc = tmp_path / "t.cpp"
+    cc.write_text('#include "gpbo.h"\nint main() { return GPBO_OK; }\n')
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.dirname(hdr), str(cc)], check=True)
