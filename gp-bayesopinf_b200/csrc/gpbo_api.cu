@@ -202,8 +202,11 @@ int plan_split(gpbo_ctx* c, cudaStream_t s, const MatArgs& a, int mode, int idx,
     }
     const long units = (long)nb * ntile;
     if (units <= 0 || nk_max < 16) return GPBO_OK;
-    int nsplit = (int)std::min<long>(16, g_sm_count / units);
-    nsplit = std::min(nsplit, nk_max / 4);
+    // tuning knobs (defaults measured on B200): at most SPLIT_MAX chunks of at least SPLIT_MIN slices
+    static const int split_max = std::getenv("GPBO_SPLIT_MAX") ? std::atoi(std::getenv("GPBO_SPLIT_MAX")) : 16;
+    static const int split_min = std::getenv("GPBO_SPLIT_MIN") ? std::max(1, std::atoi(std::getenv("GPBO_SPLIT_MIN"))) : 4;
+    int nsplit = (int)std::min<long>(split_max, g_sm_count / units);
+    nsplit = std::min(nsplit, nk_max / split_min);
     if (nsplit < 2) return GPBO_OK;
     const int chunk = (nk_max + nsplit - 1) / nsplit;
     nsplit = (nk_max + chunk - 1) / chunk;
