@@ -85,14 +85,17 @@ GPBO_HD double gpbo_exp(double x) {
 // issue bound), (ii) the flush of results below 2^-1021 done with integer selects instead of a branch.
 // NaN is NOT propagated (the result is 0): the abscissae are validated on the host (the *_host entry points reject
 // non-finite t), hyper-parameters enter through sigma^2 which multiplies every element.
+#define GPBO_EXPC_VALUES                                                                                         \
+    6755399441055744.0, 1.4426950408889634, -6.9314718055994529e-01, -2.3190468138462996e-17,                   \
+    2.4994246136424405e-08, 2.763236802746315e-07, 2.7557623140145747e-06, 2.4801486320566664e-05,              \
+    0.0001984126943145065, 0.001388888895141027, 0.008333333333560176, 0.041666666666492075,                    \
+    0.16666666666666166, 0.5000000000000018, 1.0, 1.0
 #if defined(__CUDACC__)
-static __device__ __constant__ double GPBO_EXPC[16] = {
-    6755399441055744.0, 1.4426950408889634, -6.9314718055994529e-01, -2.3190468138462996e-17,
-    2.4994246136424405e-08, 2.763236802746315e-07, 2.7557623140145747e-06, 2.4801486320566664e-05,
-    0.0001984126943145065, 0.001388888895141027, 0.008333333333560176, 0.041666666666492075,
-    0.16666666666666166, 0.5000000000000018, 1.0, 1.0};
+static __device__ __constant__ double GPBO_EXPC[16] = {GPBO_EXPC_VALUES};
+#endif
 
-__device__ __forceinline__ double gpbo_exp_neg(double x) {
+GPBO_HD double gpbo_exp_neg(double x) {
+#if defined(__CUDA_ARCH__)
     const double t = fma(x, GPBO_EXPC[1], GPBO_EXPC[0]);
     const double k = t - GPBO_EXPC[0];
     double r = fma(k, GPBO_EXPC[2], x);
@@ -105,8 +108,23 @@ __device__ __forceinline__ double gpbo_exp_neg(double x) {
     const int lo = __double2loint(p);
     const bool flush = (unsigned)(__double2hiint(x) & 0x7fffffff) > 0x40862000u;     // |x| > 708 (or NaN / inf)
     return __hiloint2double(flush ? 0 : hi, flush ? 0 : lo);
-}
+#else
+    // host restatement of the same operations, for tests/test_fastmath.py
+    static const double C[16] = {GPBO_EXPC_VALUES};
+    const double t = fma(x, C[1], C[0]);
+    const double k = t - C[0];
+    double r = fma(k, C[2], x);
+    r = fma(k, C[3], r);
+    double p = C[4];
+    for (int i = 5; i < 16; ++i) p = fma(p, r, C[i]);
+    const int64_t tb = f64_bits(t), pb = f64_bits(p), xb = f64_bits(x);
+    const int32_t ki = (int32_t)(uint32_t)(tb & 0xffffffffLL);
+    const int32_t hi = (int32_t)(uint32_t)((uint64_t)pb >> 32) + (int32_t)((uint32_t)ki << 20);
+    const uint32_t lo = (uint32_t)(pb & 0xffffffffLL);
+    const bool flush = ((uint32_t)((uint64_t)xb >> 32) & 0x7fffffffu) > 0x40862000u;
+    return flush ? 0.0 : bits_f64((int64_t)(((uint64_t)(uint32_t)hi << 32) | lo));
 #endif
+}
 
 GPBO_HD double gpbo_div(double a, double b, double rb) {
     const double q = a * rb;

@@ -35,8 +35,16 @@ SRC = textwrap.dedent(r'''
             const double a = A(rng) * A(rng), b = B(rng), q = gpbo::gpbo_div(a, b, 1.0 / b), ref = a / b;
             if (q != ref) { ++ndiff; maxd = std::fmax(maxd, std::fabs(q - ref) / (std::nextafter(ref, INFINITY) - ref)); }
         }
-        std::printf("%.6f %ld %ld %.3f %d %d\n", maxulp, bad, ndiff, maxd, gpbo::gpbo_exp(0.0) == 1.0,
-                    std::isnan(gpbo::gpbo_exp(NAN)) ? 1 : 0);
+        // the kernels' fast path (constant-bank operands, integer flush): same arithmetic as gpbo_exp for x <= 0
+        long neq = 0;
+        for (long i = 0; i < 2000000; ++i) {
+            const double x = U(rng), y = Z(rng);
+            if (gpbo::gpbo_exp_neg(x) != gpbo::gpbo_exp(x)) ++neq;
+            if (gpbo::gpbo_exp_neg(y) != gpbo::gpbo_exp(y)) ++neq;
+        }
+        if (gpbo::gpbo_exp_neg(0.0) != 1.0 || gpbo::gpbo_exp_neg(-1e9) != 0.0 || gpbo::gpbo_exp_neg(-INFINITY) != 0.0) ++neq;
+        std::printf("%.6f %ld %ld %.3f %d %d %ld\n", maxulp, bad, ndiff, maxd, gpbo::gpbo_exp(0.0) == 1.0,
+                    std::isnan(gpbo::gpbo_exp(NAN)) ? 1 : 0, neq);
     }
 ''')
 
@@ -50,6 +58,7 @@ def test_fast_exp_and_div_error(tmp_path):
     subprocess.run(["g++", "-O2", "-mfma", "-ffp-contract=off", "-I", inc, "-o", str(exe), str(src)], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
     maxulp, bad, ndiff, maxd, exp0, nan_ok = float(out[0]), int(out[1]), int(out[2]), float(out[3]), int(out[4]), int(out[5])
+    assert int(out[6]) == 0      # gpbo_exp_neg == gpbo_exp bit for bit on x <= 0 (and 0 below the flush threshold)
     assert maxulp <= 1.0         # at most 1 ulp on [-708, 0]
     assert bad == 0              # exact 0 below the flush threshold
     assert ndiff <= 20 and maxd <= 1.0   # division correctly rounded up to rare 1-ulp cases
