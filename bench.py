@@ -1,17 +1,24 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the step2_fitgps hot path (contract: see the task prompt / DESIGN.md §6).
 
-Workload (BASELINE.json configs[3]): synthetic r=64 modes x n=4096 time points x 32 hyper-parameter starts
-on one B200.  A *step* is one lock-step pass of the optimiser's inner evaluation over the whole batch:
-LML + gradient (Cholesky + K^-1 traces) for all 64 x 32 = 2048 (mode, start) pairs at their current theta.
-`value` = LML+grad evaluations per second, inputs resident in HBM.  `e2e` = the same through the host-pointer
-C-ABI call (gpbo_lml_grad_host via the ctypes layer) with pinned host buffers: H2D of (t, y, theta, gp_of) and
-D2H of (lml, grad, status) inside the timed region.  With N > 1 ranks every rank runs its own 64 x 32 batch
-(weak scaling; modes shard with no data-path collective) and all-gathers the 2048 x 4 results over NCCL.
+Primary workload (the north star's scaling target): synthetic r = 64 modes x n = 8192 time points x 32 starts, a
+FIXED GLOBAL batch of 2048 (mode, start) pairs -- the multi-start L-BFGS-B fit of all 64 GPs.  A *step* is one
+lock-step round of that fit: LML + gradient (blocked FP64 Cholesky, K^-1, gradient traces) of every pair whose
+optimiser is still running, the optimisers advanced with the results.  `--steps K` rounds are timed (each start is
+thereby bounded to K evaluations; W warm-up rounds on one wave of pairs come first), then the per-GP best start is
+selected and the posterior moments of all 64 GPs (state / ddt estimates, ddt covariance, predictive std at
+m' = n points) are computed -- timed separately and reported as `fits_per_s` beside the per-round numbers.
+
+With N > 1 ranks (torchrun) the same global batch is sharded: every rank holds the replicated optimiser pool, the
+live pairs are cut into N equal slices every round, results are all-gathered over NCCL (32 B per pair) -- STRONG
+scaling; `value` = evaluations of all ranks / time of the slowest rank.  `value` is timed with CUDA events on the
+library's stream with (t, y) resident in HBM; `e2e` is the same K rounds through the host-pointer calls timed by the
+wall clock INCLUDING the upload of (t, y) and, every round, the pinned H2D of the trial points and the D2H of the
+results.
 
 `--impl reference` times the reference's own CPU path for the same evaluation
 (GaussianProcessRegressor.log_marginal_likelihood(theta, eval_gradient=True) driven exactly as
-codebase/gpkernels.py does, through the oracle port) on the host cores, on a bounded sample.
+codebase/gpkernels.py does, through the oracle port) on the host cores, one evaluation per step.
 """
 from __future__ import annotations
 
@@ -26,26 +33,15 @@ import time
 
 import numpy as np
 
+T_START = time.time()
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-R_MODES, N_POINTS, N_STARTS = 64, 4096, 32
+R_MODES, N_POINTS, N_STARTS = 64, 8192, 32
 METRIC, UNIT = "gp_lml_grad_evals_per_sec", "evals/s"
-
-
-def workload(r, m, S, seed=0):
-    """Synthetic trajectories and one theta per (mode, start) pair, drawn log-uniformly from
-    the part of the Euler hyper-parameter box where the optimiser spends its time (all K positive definite)."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    from gp_oracle import synthetic_trajectories  # input generator shared with the golden fixtures
-
-    t, y = synthetic_trajectories(r, m, seed=seed)
-    rng = np.random.default_rng(seed + 1)
-    lo = np.log([0.3, 0.01, 1e-4])
-    hi = np.log([10.0, 0.2, 1e-1])
-    theta = rng.uniform(lo, hi, size=(r * S, 3))
-    gp_of = np.repeat(np.arange(r, dtype=np.int32), S)
-    return np.tile(t, (r, 1)), y, theta, gp_of
+WORKLOAD = ("synthetic r={r} modes x n={m} points x {S} starts, fixed global batch of {B} (mode,start) pairs "
+            "(north star scaling target; configs[3] shape at n=8192); step = one lock-step L-BFGS-B round = "
+            "LML+gradient of every live pair")
 
 
 class ClockSampler:
@@ -60,7 +56,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "500"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -98,41 +94,56 @@ def measured_peaks():
         return None
 
 
-def run_reference(args):
-    """Reference arm: the reference's CPU evaluation of the same quantity, on a bounded sample."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+def _oracle():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import gp_oracle as orc
+
+    return orc
+
+
+def _cpu_gp(t, y):
+    """The reference's CPU evaluation path (oracle port of GP_RBFW: scikit-learn regressor, alpha = 0)."""
+    orc = _oracle()
     from threadpoolctl import threadpool_info, threadpool_limits
 
     # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host core the BLAS can take
     threadpool_limits(limits=os.cpu_count())
-    T, Y, theta, gp_of = workload(R_MODES, N_POINTS, N_STARTS)
     b = np.array([(1e-5, 1e5), (1e-5, 1e2), (1e-16, 1e2)])
     gp = orc.OracleGP(tuple(b[0]), tuple(b[1]), tuple(b[2]), 0)
     gp.gpr.optimizer = None
-    gp.fit(T[0], Y[0])          # only stores the training data (no optimisation)
+    gp.fit(t, y)                # only stores the training data (no optimisation)
+    cores = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    return gp, cores
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU evaluation of the same quantity, one (mode, start) evaluation per step."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from gpbo_pkg import pkg
+
+    r, m, S = args.modes, args.points, args.starts
+    T, Y, theta, _ = pkg.workload.eval_workload(r, m, S)
+    gp, cores = _cpu_gp(T[0], Y[0])
     times = []
     for it in range(args.warmup + args.steps):
-        k = it % theta.shape[0]
         t0 = time.perf_counter()
-        gp.lml_grad(theta[k])   # one pair of the 2048-pair step
+        gp.lml_grad(theta[it % theta.shape[0]])
         dt = time.perf_counter() - t0
         if it >= args.warmup:
             times.append(dt)
     per = sum(times) / len(times)
-    cores = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
     val = 1.0 / per
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"synthetic r={R_MODES} x n={N_POINTS} x {N_STARTS} starts (BASELINE configs[3])",
-                   "sample": "1 of the 2048 (mode, start) LML+grad evaluations per step"},
+        "config": {"workload": WORKLOAD.format(r=r, m=m, S=S, B=r * S),
+                   "sample": f"one of the {r * S} (mode, start) LML+grad evaluations per step (a positive definite "
+                             "theta; the GPU arm's batch also holds the ~20 % not-PD start points, which the CPU "
+                             "path abandons after the failed Cholesky)"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "sklearn log_marginal_likelihood(theta, eval_gradient=True), m=4096, one pair per step"},
+                         "sample": f"sklearn log_marginal_likelihood(theta, eval_gradient=True), m={m}, one pair per step"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -146,8 +157,12 @@ def main():
     ap.add_argument("--modes", type=int, default=R_MODES)
     ap.add_argument("--points", type=int, default=N_POINTS)
     ap.add_argument("--starts", type=int, default=N_STARTS)
+    ap.add_argument("--m-est", type=int, default=0, help="estimation points of the moments phase (0: = points)")
+    ap.add_argument("--budget-s", type=float, default=720.0,
+                    help="secondary measurements (N = 1) are skipped once the process has run this long")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-fit-sample", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-config4", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -166,93 +181,82 @@ def main():
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=dev)
+    group = True if world > 1 else None
 
-    r, m, S = args.modes, args.points, args.starts
-    T, Y, theta, gp_of = workload(r, m, S, seed=rank)      # every rank: its own r modes (weak scaling)
-    B = theta.shape[0]
+    r, m, S, K, W = args.modes, args.points, args.starts, args.steps, args.warmup
+    T, Y, bl, starts, gp_of = pkg.workload.fit_workload(r, m, S)           # the same global batch on every rank
+    B = starts.shape[0]
     ctx = pkg.default_context(local)
-
-    # device-resident inputs/outputs (torch = allocator + address carrier)
-    Td, Yd, thd = (torch.as_tensor(x, device=dev) for x in (T, Y, theta))
-    gpd = torch.as_tensor(gp_of, device=dev)
-    res = torch.empty((B, 4), dtype=torch.float64, device=dev)      # [lml, grad(3)] per pair
-    lml_d, grad_d = torch.empty(B, dtype=torch.float64, device=dev), torch.empty((B, 3), dtype=torch.float64, device=dev)
-    st_d = torch.empty(B, dtype=torch.int32, device=dev)
-    gathered = torch.empty((world * B, 4), dtype=torch.float64, device=dev) if world > 1 else None
-    stream = torch.cuda.current_stream(dev)
-
-    def step_device():
-        ctx.lml_grad_device(Td.data_ptr(), Yd.data_ptr(), r, m, thd.data_ptr(), gpd.data_ptr(), B, lml_d.data_ptr(),
-                            grad_d.data_ptr(), st_d.data_ptr(), stream.cuda_stream)
-        if world > 1:
-            res[:, 0] = lml_d
-            res[:, 1:] = grad_d
-            dist.all_gather_into_tensor(gathered, res)
-
-    # pinned host buffers for the end-to-end arm
-    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
-    Th, Yh, thh, gph = pin(T), pin(Y), pin(theta), pin(gp_of)
-
-    def step_host():
-        return ctx.lml_grad(Th, Yh, thh, gph)
+    lib_stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        w0 = time.perf_counter()
-        for _ in range(steps):
-            fn()
-        e1.record(stream)
-        barrier()
-        wall = time.perf_counter() - w0
-        ms = max(e0.elapsed_time(e1), 0.0)
-        # the C ABI synchronises its stream before returning, so event time == wall time up to launch overheads;
-        # take the max so copies issued on the library's own stream (host arm) are covered too
-        ms = max(ms, wall * 1e3) if fn is step_host else ms
-        if world > 1:
-            tt = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            ms = float(tt.item())
-        return ms
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        tt = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
 
     # FP64 tensor-pipe peak (DMMA issue rate), measured live: MEASURED_PEAKS.json has no FP64 entry
     dmma_peak, _ = ctx.dmma_peak(100000)
 
-    for _ in range(args.warmup):
-        step_device()
+    # ---- warm-up: W rounds of one wave of pairs (kernels loaded, workspace allocated, clocks up) -------------------
+    ctx.upload_problem(T, Y)
+    nwarm = max(1, min(B // world, ctx.wave_capacity(m), 148))
+    pd_theta = pkg.workload.eval_workload(r, m, S)[2]
+    for _ in range(max(W, 1)):
+        ctx.lml_grad_resident(pd_theta[:nwarm], gp_of[:nwarm])
+
+    # ---- timed: K lock-step rounds of the global fit ------------------------------------------------------------
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = ctx.launch_count
     ctx.profile_enable(True)
-    ms = timed(step_device, args.steps)
+    live = []
+    barrier()
+    w_e2e0 = time.perf_counter()
+    ctx.upload_problem(T, Y)                       # e2e: the H2D of (t, y) is inside; the device-timed value starts after it
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(lib_stream)
+    res = pkg.sharding.fit_pairs(ctx, T, Y, bl, starts, gp_of, group=group, max_rounds=K, stats=live)
+    e1.record(lib_stream)
+    barrier()
+    wall_e2e = time.perf_counter() - w_e2e0
     prof = ctx.profile_get()
     ctx.profile_enable(False)
     launches = ctx.launch_count - launches0
     clocks = sampler.stop()
-    ok = int((st_d == 0).sum().item())
-    ms_per_step = ms / args.steps
-    value = world * B / (ms_per_step * 1e-3)
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    wall_e2e = max_over_ranks(wall_e2e)
+    rounds = len(live)
+    evals = int(sum(live))
+    ms_per_step = ms / max(rounds, 1)
+    value = evals / (ms * 1e-3)
+    e2e = evals / wall_e2e
 
-    # end-to-end through the host-pointer C-ABI call
-    step_host()
-    ms_h = timed(step_host, max(1, min(args.steps, 2))) / max(1, min(args.steps, 2))
-    e2e = world * B / (ms_h * 1e-3)
-    h2d = Th.nbytes + Yh.nbytes + thh.nbytes + gph.nbytes
-    d2h = B * (8 + 24 + 4)
+    # ---- per-GP selection + posterior moments of all GPs (timed separately; fits/s) ---------------------------------
+    funs = np.where(np.isfinite(res["fun"]), res["fun"], np.inf).reshape(r, S)
+    theta_sel = res["theta"].reshape(r, S, 3)[np.arange(r), funs.argmin(1)]
+    n_est = args.m_est or m
+    t_est = np.linspace(0.0, 1.0, n_est)
+    barrier()
+    w0 = time.perf_counter()
+    mom = pkg.sharding.moments(ctx, T, Y, theta_sel, t_est, group=group, want_cov=True, keep_cov=False)
+    own = pkg.sharding.shard_indices(r, rank, world)
+    if own.size:
+        ctx.predict(T[own], Y[own], theta_sel[own], t_est)               # predictive mean / std (gpkernels.py:350-365)
+    barrier()
+    t_mom = max_over_ranks(time.perf_counter() - w0)
+    fits_per_s = r / (wall_e2e + t_mom)
 
-    # roofline of the dominant kernel class, per launch: algorithmic flops = m_pad^3/3 per pair for each
-    # of potrf (diag+panel), trtri, lauum; "issued" = DMMA flops the 128-tile schedule actually executes.
+    # ---- roofline of the dominant kernel class -------------------------------------------------------
     T_blocks = (m + 127) // 128
     m_pad = T_blocks * 128
     blk = 2.0 * 128 ** 3
-    # structural-zero skipping (tile_engine.cuh): symmetric diagonal tiles issue 136/256 of their 8x8 blocks; a k-block
-    # with a triangular block inverse as row operand issues 36/64, as column operand 40/64 of its DMMAs
     SYM, TRI_A, TRI_B = 136.0 / 256.0, 36.0 / 64.0, 40.0 / 64.0
     issued_pp = {
         "chol_diag": blk * SYM * sum(j for j in range(T_blocks)),
@@ -260,55 +264,84 @@ def main():
         "trtri": blk * sum((i - j - 1) + TRI_B + TRI_A for i in range(1, T_blocks) for j in range(i)),
         "lauum_grad": blk * sum(i * ((T_blocks - i - 1) + TRI_A) + SYM * (T_blocks - i) for i in range(T_blocks)),
     }
+    local_evals = int(res.get("local_evals", evals))
     dom = max(("chol_panel", "trtri", "lauum_grad"), key=lambda k: prof[k][0])
-    cap = min(B, ctx.wave_capacity(m))
-    waves = [min(cap, B - w0) for w0 in range(0, B, cap)]
     flops_third = float(m_pad) ** 3 / 3.0
     launches_dom = max(prof[dom][1], 1)
-    total_flops_dom = flops_third * B * args.steps   # all launches of that class over the timed region
-    dom_ms = prof[dom][0] + (prof["chol_diag"][0] if dom == "chol_panel" else 0.0)   # potrf = diag + panel
-    achieved = total_flops_dom / (dom_ms * 1e-3) / 1e12
+    total_flops_dom = flops_third * local_evals        # all launches of that class over the timed region, this rank
+    dom_ms = prof[dom][0] + (prof["chol_diag"][0] if dom == "chol_panel" else 0.0)      # potrf = diag + panel
+    achieved = total_flops_dom / (max(dom_ms, 1e-9) * 1e-3) / 1e12
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dom)
     except Exception:
         pass
+    kernel_total_ms = sum(v[0] for v in prof.values())
     roofline = {
         "bound": "tensor", "kernel": dom, "achieved": achieved, "peak": dmma_peak, "unit": "TFLOP/s",
         "frac": achieved / dmma_peak, "traffic": traffic,
         "peak_source": "FP64 DMMA issue-rate micro-benchmark run in this process (gpbo_bench_dmma_peak); "
-                       "MEASURED_PEAKS.json holds no FP64 figure",
+                       "MEASURED_PEAKS.json holds no FP64 figure; cuBLAS DGEMM rate beside it in dgemm_cublas_tflops",
         "flops_per_launch": total_flops_dom / launches_dom, "avg_launch_ms": dom_ms / launches_dom,
-        "share_of_step": prof[dom][0] / sum(v[0] for v in prof.values()),
-        "whole_eval_tflops": world * B * float(m) ** 3 / (ms_per_step * 1e-3) / 1e12,
-        "whole_eval_frac": B * float(m) ** 3 / (ms_per_step * 1e-3) / 1e12 / dmma_peak,
-        "dmma_issued_tflops": {k: issued_pp[k] * B * args.steps / (prof[k][0] * 1e-3) / 1e12
+        "share_of_step": prof[dom][0] / max(kernel_total_ms, 1e-9),
+        "whole_eval_tflops": evals * float(m) ** 3 / (ms * 1e-3) / 1e12,
+        "whole_eval_frac": evals * float(m) ** 3 / (ms * 1e-3) / 1e12 / (dmma_peak * world),
+        "kernel_time_share_of_wall": kernel_total_ms / max(e0.elapsed_time(e1), 1e-9),
+        "dmma_issued_tflops": {k: issued_pp[k] * local_evals / (prof[k][0] * 1e-3) / 1e12
                                for k in issued_pp if prof[k][0] > 0},
         "kernel_ms": {k: round(v[0], 3) for k, v in prof.items() if v[1]},
-        "waves": waves,
+        "rank": rank,
     }
 
+    h2d_round = 28.0 * evals / max(rounds, 1) / world       # theta (24 B) + gp_of (4 B) per live pair, per rank
+    d2h_round = 36.0 * evals / max(rounds, 1) / world       # lml (8) + grad (24) + status (4)
     out = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": rounds, "warmup": W,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"synthetic r={r} modes x n={m} points x {S} starts per GPU (BASELINE configs[3]); "
-                               "step = LML+gradient of all r*S (mode,start) pairs",
-                   "pairs_per_gpu": B, "l2": "inputs larger than L2 (each pair's 128 MiB factor streams from HBM)",
-                   "status_ok_pairs": ok},
+        "config": {"workload": WORKLOAD.format(r=r, m=m, S=S, B=B), "global_pairs": B,
+                   "live_pairs_per_round": live, "evaluations": evals,
+                   "sharding": "replicated optimiser pool; live pairs re-cut into N equal slices every round; "
+                               "all-gather of [lml, grad] (32 B / pair) over NCCL" if world > 1 else "single GPU",
+                   "l2": "inputs larger than L2 (each pair's 512 MiB factor streams from HBM)",
+                   "waves_per_round_per_rank": -(-(-(-max(live) // world)) // max(ctx.wave_capacity(m), 1)) if live else 0,
+                   "warmup_rounds": f"{max(W, 1)} rounds of {nwarm} pairs (one wave) before the timed region"},
         "clocks": clocks, "gpu_launches": int(launches),
-        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": ms_h},
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d_round), "d2h_bytes_per_step": int(d2h_round),
+                "h2d_bytes_once": int(T.nbytes + Y.nbytes), "seconds": wall_e2e,
+                "note": "same K rounds by wall clock, including the upload of (t, y) and the per-round pinned H2D / D2H"},
+        "fits_per_s": fits_per_s,
+        "fit": {"gps": r, "starts_per_gp": S, "rounds": rounds, "seconds_rounds": wall_e2e, "seconds_moments": t_mom,
+                "m_est": n_est, "bounded": f"each start bounded to {K} evaluations (--steps); posterior moments "
+                                           "(state, ddt, ddt covariance, predictive mean/std) of all GPs included, sqrtW excluded (SURVEY 8d)",
+                "best_lml_first4": (-funs.min(1))[:4].tolist(),
+                "running_after_K": int((res["status"] == -1).sum()), "not_pd_at_start": int((res["status"] == 5).sum()),
+                "moments_status_ok": int((mom["status"] == 0).sum())},
         "roofline": roofline,
     }
 
-    if rank == 0 and world == 1 and not args.no_fit_sample:
-        out["roofline_assembly"] = assembly_roofline(ctx, dev)
-        out["fit_sample"] = fit_sample(ctx, m)
-        out["fit_reference_configs"] = fit_reference_configs(ctx)
-        out["moments_sample"] = moments_sample(ctx, m)
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(T, Y, theta)
+    def have_time():
+        return (time.time() - T_START) < args.budget_s
+
+    if world > 1 and not args.no_config4:
+        out["config4_sample"] = config4_sample(pkg, ctx, dist, rank, world, dev, dmma_peak, barrier, max_over_ranks)
+    if rank == 0 and world == 1 and not args.no_extras:
+        extras = (("dgemm_cublas_tflops", lambda: dgemm_rate(dev)),
+                  ("evals_configs3", lambda: evals_configs3(pkg, ctx, dev, dmma_peak)),
+                  ("roofline_assembly", lambda: assembly_roofline(ctx, dev)),
+                  ("roofline_prediction", lambda: prediction_roofline(pkg, ctx, dmma_peak)),
+                  ("fit_reference_configs", lambda: fit_reference_configs(ctx)),
+                  ("fit_sample", lambda: fit_sample(pkg, ctx)))
+        for name, fn in extras:
+            if not have_time():
+                out[name] = "skipped: time budget"
+                continue
+            try:
+                out[name] = fn()
+            except Exception as exc:  # a secondary measurement must never lose the headline line
+                out[name] = f"failed: {type(exc).__name__}: {exc}"
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and have_time():
+        out["cpu_baseline"] = cpu_baseline(pkg, T, Y, m)
     elif rank == 0:
         out["cpu_baseline"] = None
     if rank == 0:
@@ -317,15 +350,94 @@ def main():
         dist.destroy_process_group()
 
 
-def fit_sample(ctx, m, r=4, S=32):
-    """Measured GP fits/s on a bounded sub-workload: r modes x S starts, full L-BFGS-B + posterior moments."""
-    T, Y, _, gp_of = workload(r, m, S, seed=123)
-    b = np.log(np.array([(1e-5, 1e5), (1e-5, 1e2), (1e-16, 1e2)]))
-    rng = np.random.default_rng(7)
-    starts = rng.uniform(b[:, 0], b[:, 1], size=(r * S, 3))
-    starts[::S] = 0.0
+def dgemm_rate(dev, n=8192):
+    """cuBLAS DGEMM n^3 through torch.matmul: the library's achievable FP64 rate, beside the DMMA issue peak."""
+    import torch
+
+    a = torch.randn((n, n), dtype=torch.float64, device=dev)
+    b = torch.randn((n, n), dtype=torch.float64, device=dev)
+    torch.matmul(a, b)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    e0.record()
+    for _ in range(3):
+        torch.matmul(a, b)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    return 3 * 2.0 * n ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
+
+
+def evals_configs3(pkg, ctx, dev, dmma_peak, r=64, m=4096, S=32, steps=2):
+    """BASELINE configs[3] on one B200 (last round's headline, kept as a secondary key): LML + gradient of all
+    64 x 32 pairs at fixed theta, device-resident, CUDA events on the launching stream."""
+    import torch
+
+    T, Y, theta, gp_of = pkg.workload.eval_workload(r, m, S)
+    B = theta.shape[0]
+    Td, Yd, thd = (torch.as_tensor(x, device=dev) for x in (T, Y, theta))
+    gpd = torch.as_tensor(gp_of, device=dev)
+    lml_d = torch.empty(B, dtype=torch.float64, device=dev)
+    grad_d = torch.empty((B, 3), dtype=torch.float64, device=dev)
+    st_d = torch.empty(B, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def step():
+        ctx.lml_grad_device(Td.data_ptr(), Yd.data_ptr(), r, m, thd.data_ptr(), gpd.data_ptr(), B, lml_d.data_ptr(),
+                            grad_d.data_ptr(), st_d.data_ptr(), stream.cuda_stream)
+
+    step()
+    ctx.profile_enable(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    prof = ctx.profile_get()
+    ctx.profile_enable(False)
+    ms = e0.elapsed_time(e1) / steps
+    third = float(m) ** 3 / 3.0 * B * steps
+    cls = {"potrf": prof["chol_diag"][0] + prof["chol_panel"][0], "trtri": prof["trtri"][0],
+           "lauum_grad": prof["lauum_grad"][0]}
+    return {"workload": f"r={r} x n={m} x {S} starts, fixed theta, one step = all {B} pairs", "evals_per_s": B / (ms * 1e-3),
+            "ms_per_step": ms, "whole_eval_frac": B * float(m) ** 3 / (ms * 1e-3) / 1e12 / dmma_peak,
+            "class_frac_algorithmic": {k: third / (v * 1e-3) / 1e12 / dmma_peak for k, v in cls.items() if v > 0},
+            "kernel_ms_per_step": {k: round(v[0] / steps, 3) for k, v in prof.items() if v[1]},
+            "status_ok_pairs": int((st_d == 0).sum().item())}
+
+
+def config4_sample(pkg, ctx, dist, rank, world, dev, dmma_peak, barrier, max_over_ranks, r=8, m=16384, S=32, K=4):
+    """BASELINE configs[4]'s shape (n = 16384, 32 starts) with the mode count reduced from 256 to 8 so that it fits
+    the bench's time budget: K lock-step rounds of the sharded fit (same code path as the primary workload)."""
+    import torch
+
+    T, Y, bl, starts, gp_of = pkg.workload.fit_workload(r, m, S, seed=4)
+    live = []
+    ctx.upload_problem(T, Y)
+    th = pkg.workload.eval_workload(r, m, S, seed=4)[2]
+    ctx.lml_grad_resident(th[:4], gp_of[:4])                      # allocation / warm-up
+    lib_stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(lib_stream)
+    pkg.sharding.fit_pairs(ctx, T, Y, bl, starts, gp_of, group=True, max_rounds=K, stats=live)
+    e1.record(lib_stream)
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    evals = int(sum(live))
+    return {"workload": f"configs[4] shape: n={m} x {S} starts, modes reduced 256 -> {r} (stated), {K} rounds, "
+                        f"{r * S} pairs sharded over {world} GPUs", "evals_per_s": evals / (ms * 1e-3),
+            "seconds": ms * 1e-3, "live_pairs_per_round": live,
+            "whole_eval_frac": evals * float(m) ** 3 / (ms * 1e-3) / 1e12 / (dmma_peak * world)}
+
+
+def fit_sample(pkg, ctx, r=4, m=4096, S=32):
+    """Measured GP fits/s to CONVERGENCE on a bounded sub-workload: r modes x S starts, full L-BFGS-B + posterior
+    moments (state, ddt, covariance, predictive mean/std; sqrtW excluded per SURVEY 8d)."""
+    T, Y, bl, starts, gp_of = pkg.workload.fit_workload(r, m, S, seed=123)
     t0 = time.perf_counter()
-    res = ctx.fit(T, Y, b, starts, gp_of)
+    res = ctx.fit(T, Y, bl, starts, gp_of)
     t_fit = time.perf_counter() - t0
     funs = np.where(np.isfinite(res["fun"]), res["fun"], np.inf).reshape(r, S)
     best = res["theta"].reshape(r, S, 3)[np.arange(r), funs.argmin(1)]
@@ -335,35 +447,91 @@ def fit_sample(ctx, m, r=4, S=32):
     t_mom = time.perf_counter() - t1
     return {"modes": r, "starts": S, "m": m, "m_est": m, "fit_seconds": t_fit, "moments_seconds": t_mom,
             "fits_per_s": r / (t_fit + t_mom), "lml_grad_evals": res["evals"], "rounds": res["rounds"],
-            "best_lml": (-funs.min(1)).tolist()}
+            "evals_per_s_over_fit": res["evals"] / t_fit, "best_lml": (-funs.min(1)).tolist()}
 
 
-def assembly_roofline(ctx, dev, n=8192, B=8):
-    """HBM-write roofline of the stand-alone kernel-matrix assembly (train K, sklearn order): 8 B per element."""
+def assembly_roofline(ctx, dev):
+    """HBM-write roofline of the stand-alone kernel-matrix assembly: 8 B per element, EVERY kind, the symmetric and the
+    general kernel, at 8 x 8192^2, 2 x 16384^2 and the reference's own m' >> m shape (3200 x 200)."""
     import torch
 
     peaks = measured_peaks() or {}
     peak = float(peaks.get("hbm_gbs", 6543.1))
-    t = torch.sort(torch.rand(B, n, dtype=torch.float64, device=dev), dim=1).values.contiguous()
-    th = torch.log(torch.tensor([[1.5, 0.05, 1e-2]], dtype=torch.float64, device=dev)).repeat(B, 1).contiguous()
-    o = torch.empty((B, n, n), dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream(dev)
+    names = {0: "K_train", 1: "K_yy", 2: "K_cross", 3: "kappa", 4: "K_zy", 5: "K_zz", 6: "dK_dlogell"}
     res = {}
-    for name, kind, other in (("train_K_symmetric", 0, t), ("cross_K_general", 2, t.clone())):
-        args = (kind, t.data_ptr(), n, n, other.data_ptr(), n, n, th.data_ptr(), B, o.data_ptr(), stream.cuda_stream)
-        ctx.assemble_device(*args)
+
+    def run(kind, t1, t2, th, o, n1, n2, B, reps):
+        a = (kind, t1.data_ptr(), n1, n1, t2.data_ptr(), n2, n2, th.data_ptr(), B, o.data_ptr(), stream.cuda_stream)
+        ctx.assemble_device(*a)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize(dev)
         e0.record(stream)
-        for _ in range(5):
-            ctx.assemble_device(*args)
+        for _ in range(reps):
+            ctx.assemble_device(*a)
         e1.record(stream)
         torch.cuda.synchronize(dev)
-        gbs = 5 * B * n * n * 8 / (e0.elapsed_time(e1) * 1e-3) / 1e9
-        res[name] = {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
-                     "bytes_per_launch": B * n * n * 8, "shape": [B, n, n]}
-    res["peak_source"] = "MEASURED_PEAKS.json hbm_gbs (burst copy bandwidth)" if peaks else "fallback 6543.1 GB/s"
-    return res
+        return reps * B * n1 * n2 * 8 / (e0.elapsed_time(e1) * 1e-3) / 1e9
+
+    for label, B, n1, n2, reps in (("8x8192x8192", 8, 8192, 8192, 3), ("2x16384x16384", 2, 16384, 16384, 3),
+                                   ("64x3200x200", 64, 3200, 200, 20)):
+        t1 = torch.sort(torch.rand(B, n1, dtype=torch.float64, device=dev), dim=1).values.contiguous()
+        t2 = t1.clone() if n1 == n2 else torch.sort(torch.rand(B, n2, dtype=torch.float64, device=dev), dim=1).values.contiguous()
+        th = torch.log(torch.tensor([[1.5, 0.05, 1e-2]], dtype=torch.float64, device=dev)).repeat(B, 1).contiguous()
+        o = torch.empty((B, n1, n2), dtype=torch.float64, device=dev)
+        for kind in range(7):
+            if n1 != n2 and kind in (0, 1, 5, 6):
+                continue                      # square-only kinds
+            gen = run(kind, t1, t2, th, o, n1, n2, B, reps)
+            res[f"{names[kind]}_general_{label}"] = round(gen / peak, 4)
+            if n1 == n2:
+                sym = run(kind, t1, t1, th, o, n1, n2, B, reps)
+                res[f"{names[kind]}_symmetric_{label}"] = round(sym / peak, 4)
+        del o
+    fr = [v for v in res.values()]
+    return {"bound": "hbm", "unit": "fraction of peak GB/s", "peak": peak, "bytes_per_element": 8,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy bandwidth)" if peaks else "fallback 6543.1 GB/s",
+            "min_frac": min(fr), "frac": res}
+
+
+def prediction_roofline(pkg, ctx, dmma_peak, G=8, m=4096):
+    """compute_lstsq_matrices + predict for G GPs at m = m': per-class device time against the bound of each class --
+    FP64 tensor peak for the Cholesky / prediction TRSM (m^2 m' flops) / Schur complement (m m'^2 flops), FP64 issue
+    + HBM for the fused mean / std kernels, Newton-Schulz sqrtW as issued DMMA TFLOP/s."""
+    T, Y, _, _ = pkg.workload.eval_workload(G, m, 1, seed=321)
+    theta = np.tile(np.log([1.5, 0.05, 1e-2]), (G, 1))
+    t_est = np.linspace(0, 1, m)
+    ctx.lstsq_weights(T[:1], Y[:1], theta[:1], t_est, 1e-8)          # warm-up / allocation
+    ctx.profile_enable(True)
+    t0 = time.perf_counter()
+    state, ddt, cov, w, st, wst, wit = ctx.lstsq_weights(T, Y, theta, t_est, 1e-8)
+    dt = time.perf_counter() - t0
+    prof = ctx.profile_get()
+    ctx.profile_enable(False)
+    ctx.profile_enable(True)
+    ctx.predict(T, Y, theta, t_est)
+    prof_p = ctx.profile_get()
+    ctx.profile_enable(False)
+    A = cov[0] + 1e-8 * np.eye(m)
+    x = np.random.default_rng(0).standard_normal(m)
+    resid = float(np.abs(w[0] @ (A @ (w[0] @ x)) - x).max() / np.abs(x).max())     # sqrtW (C + eta I) sqrtW x = x
+    T_blocks = (m + 127) // 128
+    ns_flops = float(wit.max() + 1) * G * 2.0 * 128 ** 3 * T_blocks * (T_blocks ** 2 + T_blocks * (T_blocks + 1))
+    mp = T_blocks * 128
+    tf = lambda flops, ms: flops / (ms * 1e-3) / 1e12 if ms > 0 else None
+    trsm = tf(G * float(mp) ** 3, prof["cross_panel"][0])
+    schur = tf(G * float(mp) ** 3, prof["schur"][0])
+    return {"gps": G, "m": m, "m_est": m, "host_call_seconds": dt,
+            "device_ms": {k: round(v[0], 3) for k, v in prof.items() if v[1]},
+            "predict_device_ms": {k: round(v[0], 3) for k, v in prof_p.items() if v[1]},
+            "trsm": {"bound": "tensor", "achieved": trsm, "peak": dmma_peak, "unit": "TFLOP/s",
+                     "frac": trsm / dmma_peak if trsm else None, "flops": "m^2 m' per GP"},
+            "schur": {"bound": "tensor", "achieved": schur, "peak": dmma_peak, "unit": "TFLOP/s",
+                      "frac": schur / dmma_peak if schur else None, "flops": "m m'^2 per GP"},
+            "mean_std_ms": prof["mean_std"][0],
+            "sqrtw_iterations": int(wit.max()), "sqrtw_status_ok": int((wst == 0).sum()),
+            "sqrtw_ms": prof["sqrtw"][0], "sqrtw_identity_residual": resid,
+            "sqrtw_dmma_issued_tflops": tf(ns_flops, prof["sqrtw"][0])}
 
 
 def fit_reference_configs(ctx):
@@ -381,68 +549,40 @@ def fit_reference_configs(ctx):
         starts = np.zeros((G, S, 3))
         starts[:, 1:] = g["starts"]
         gp_of = np.repeat(np.arange(G, dtype=np.int32), S)
-        t0 = time.perf_counter()
-        res = ctx.fit(T, Y, bl, starts.reshape(-1, 3), gp_of)
-        funs = np.where(np.isfinite(res["fun"]), res["fun"], np.inf).reshape(G, S)
-        best = res["theta"].reshape(G, S, 3)[np.arange(G), funs.argmin(1)]
-        ctx.lstsq_moments(T, Y, best, t_est)
-        ctx.predict(T, Y, best, t_est)
-        dt = time.perf_counter() - t0
+        best_dt, res = None, None
+        for _ in range(2):                       # second run: kernels loaded, buffers allocated
+            t0 = time.perf_counter()
+            res = ctx.fit(T, Y, bl, starts.reshape(-1, 3), gp_of)
+            funs = np.where(np.isfinite(res["fun"]), res["fun"], np.inf).reshape(G, S)
+            best = res["theta"].reshape(G, S, 3)[np.arange(G), funs.argmin(1)]
+            t1 = time.perf_counter()
+            ctx.lstsq_moments(T, Y, best, t_est)
+            ctx.predict(T, Y, best, t_est)
+            dt = time.perf_counter() - t0
+            fit_dt = t1 - t0
+            best_dt = dt if best_dt is None else min(best_dt, dt)
         lml = -funs.min(1)
         out[name] = {"gps": int(G), "m": int(T.shape[1]), "m_est": int(t_est.size), "starts": int(S),
-                     "seconds": dt, "fits_per_s": G / dt, "lml_grad_evals": res["evals"], "rounds": res["rounds"],
+                     "seconds": best_dt, "fit_seconds": fit_dt, "fits_per_s": G / best_dt,
+                     "lml_grad_evals": res["evals"], "longest_chain": res["rounds"],
                      "max_rel_lml_gap_vs_reference": float(np.max((g["lml_opt"] - lml) / np.abs(g["lml_opt"]))),
                      "reference_cpu_fit_seconds": float(np.sum(g["fit_seconds"]))}
     return out
 
 
-def moments_sample(ctx, m, G=8):
-    """compute_lstsq_matrices for G GPs at m = m' (state, ddt, ddt covariance, sqrtW by Newton-Schulz): host-call wall
-    time (includes the D2H of two m'^2 matrices per GP) and per-class device milliseconds."""
-    T, Y, _, _ = workload(G, m, 1, seed=321)
-    theta = np.tile(np.log([1.5, 0.05, 1e-2]), (G, 1))
-    t_est = np.linspace(0, 1, m)
-    ctx.lstsq_weights(T[:1], Y[:1], theta[:1], t_est, 1e-8)          # warm-up / allocation
-    ctx.profile_enable(True)
-    t0 = time.perf_counter()
-    state, ddt, cov, w, st, wst, wit = ctx.lstsq_weights(T, Y, theta, t_est, 1e-8)
-    dt = time.perf_counter() - t0
-    prof = ctx.profile_get()
-    ctx.profile_enable(False)
-    A = cov[0] + 1e-8 * np.eye(m)
-    x = np.random.default_rng(0).standard_normal(m)
-    resid = float(np.abs(w[0] @ (A @ (w[0] @ x)) - x).max() / np.abs(x).max())     # sqrtW (C + eta I) sqrtW x = x
-    T_blocks = (m + 127) // 128
-    ns_flops = float(wit.max() + 1) * G * 2.0 * 128 ** 3 * T_blocks * (T_blocks ** 2 + T_blocks * (T_blocks + 1))
-    return {"gps": G, "m": m, "m_est": m, "seconds": dt, "device_ms": {k: round(v[0], 3) for k, v in prof.items() if v[1]},
-            "sqrtw_iterations": int(wit.max()), "sqrtw_status_ok": int((wst == 0).sum()),
-            "sqrtw_identity_residual": resid,
-            "sqrtw_dmma_issued_tflops": ns_flops / (prof["sqrtw"][0] * 1e-3) / 1e12 if prof["sqrtw"][0] > 0 else None}
-
-
-def cpu_baseline(T, Y, theta, budget_s=20.0):
+def cpu_baseline(pkg, T, Y, m):
     """Oracle port (sklearn-driven, as the reference) timed on this box's host cores, bounded sample."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import gp_oracle as orc
-    from threadpoolctl import threadpool_info, threadpool_limits
-
-    threadpool_limits(limits=os.cpu_count())
-    b = np.array([(1e-5, 1e5), (1e-5, 1e2), (1e-16, 1e2)])
-    gp = orc.OracleGP(tuple(b[0]), tuple(b[1]), tuple(b[2]), 0)
-    gp.gpr.optimizer = None
-    gp.fit(T[0], Y[0])
-    times, k = [], 0
-    t_start = time.perf_counter()
-    while (time.perf_counter() - t_start < budget_s and k < 4) or k < 2:
+    theta = pkg.workload.eval_workload(2, m, 2)[2]
+    gp, cores = _cpu_gp(T[0], Y[0])
+    times = []
+    for k in range(2):
         t0 = time.perf_counter()
         gp.lml_grad(theta[k])
         times.append(time.perf_counter() - t0)
-        k += 1
-    per = min(times[1:]) if len(times) > 1 else times[0]
-    cores = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    per = min(times)
     return {"value": 1.0 / per, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{k} single-pair LML+grad evaluations at m={T.shape[1]} via sklearn "
-                      "GaussianProcessRegressor.log_marginal_likelihood (best of the non-first)",
+            "sample": f"2 single-pair LML+grad evaluations at m={m} via sklearn "
+                      "GaussianProcessRegressor.log_marginal_likelihood (the faster of the two)",
             "host_cpus": os.cpu_count()}
 
 

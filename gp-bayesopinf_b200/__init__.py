@@ -10,7 +10,7 @@ Public surface (mirrors the reference):
   _lib.Context                           -- ctypes handle on libgpbo.so (C ABI in include/gpbo.h)
 """
 
-from . import _lib, gpkernels, sharding, step2_fitgps  # noqa: F401
+from . import _lib, gpkernels, sharding, step2_fitgps, workload  # noqa: F401
 from ._lib import Context, GpboError, default_context  # noqa: F401
 from .gpkernels import GP_MaternW, GP_RBFW  # noqa: F401
 from .step2_fitgps import fit_gaussian_processes, fit_gaussian_processes_multi  # noqa: F401

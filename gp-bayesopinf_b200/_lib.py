@@ -15,9 +15,9 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgpbo.so")
 
-NCLASS = 12
+NCLASS = 13
 KERNEL_CLASSES = ("prep", "chol_diag", "chol_panel", "trsv", "trtri", "lauum_grad", "finalize",
-                  "cross_panel", "schur", "mean_std", "assemble", "sqrtw")
+                  "cross_panel", "schur", "mean_std", "assemble", "sqrtw", "small")
 
 EXPORTS = (
     "gpbo_version", "gpbo_last_error", "gpbo_create", "gpbo_destroy", "gpbo_launch_count",
@@ -25,7 +25,9 @@ EXPORTS = (
     "gpbo_predict_host", "gpbo_lstsq_moments_host", "gpbo_lstsq_moments", "gpbo_profile_enable",
     "gpbo_profile_get", "gpbo_bench_dmma_peak", "gpbo_lbfgsb_minimize", "gpbo_sqrtw", "gpbo_sqrtw_host",
     "gpbo_lstsq_weights_host", "gpbo_assemble_matern", "gpbo_set_kernel_family",
-    "gpbo_weighted_products_host",
+    "gpbo_weighted_products_host", "gpbo_set_small_path", "gpbo_optpool_create", "gpbo_optpool_destroy",
+    "gpbo_optpool_live", "gpbo_optpool_feed", "gpbo_optpool_result", "gpbo_problem_upload_host",
+    "gpbo_lml_grad_resident_host", "gpbo_get_stream",
 )
 
 
@@ -74,6 +76,15 @@ def load():
     lib.gpbo_lstsq_weights_host.argtypes = [vp, dp, dp, C.c_int, C.c_int, dp, dp, C.c_long, C.c_int, C.c_double, dp, dp,
                                             dp, dp, ip, ip, ip]
     lib.gpbo_weighted_products_host.argtypes = [vp, dp, C.c_int, C.c_int, dp, C.c_int, dp, dp, dp]
+    lib.gpbo_set_small_path.argtypes = [vp, C.c_int]
+    lib.gpbo_get_stream.argtypes = [vp, C.POINTER(vp)]
+    lib.gpbo_optpool_create.argtypes = [C.POINTER(vp), C.c_int, dp, dp, dp]
+    lib.gpbo_optpool_destroy.argtypes = [vp]
+    lib.gpbo_optpool_live.argtypes = [vp, ip, dp, ip]
+    lib.gpbo_optpool_feed.argtypes = [vp, C.c_int, ip, dp, dp]
+    lib.gpbo_optpool_result.argtypes = [vp, dp, dp, ip, ip, ip, C.POINTER(C.c_longlong), ip]
+    lib.gpbo_problem_upload_host.argtypes = [vp, dp, dp, C.c_int, C.c_int]
+    lib.gpbo_lml_grad_resident_host.argtypes = [vp, dp, ip, C.c_int, dp, dp, ip]
     lib.gpbo_profile_enable.argtypes = [vp, C.c_int]
     lib.gpbo_profile_get.argtypes = [vp, dp, C.POINTER(C.c_longlong)]
     lib.gpbo_bench_dmma_peak.argtypes = [vp, C.c_int, dp, dp]
@@ -106,6 +117,91 @@ def _f64(a, shape=None):
     return a
 
 
+def _problem(t, y, theta=None, n_theta=None):
+    """Validate the (t, y[, theta]) arguments the way scikit-learn validates X / y (``ValueError`` on inconsistent
+    numbers of samples) -- the C side reads G*m doubles from each of t and y and 3 per theta row."""
+    t, y = _f64(np.atleast_2d(t)), _f64(np.atleast_2d(y))
+    if t.ndim != 2 or y.shape != t.shape:
+        raise ValueError(f"Found input variables with inconsistent numbers of samples: t {t.shape}, y {y.shape}")
+    if t.shape[1] == 0:
+        raise ValueError("at least one training sample is required")
+    if theta is None:
+        return t, y
+    theta = _f64(np.atleast_2d(theta))
+    if theta.ndim != 2 or theta.shape[1] != 3 or (n_theta is not None and theta.shape[0] != n_theta):
+        want = "(B, 3)" if n_theta is None else f"({n_theta}, 3)"
+        raise ValueError(f"theta must have shape {want}, got {theta.shape}")
+    return t, y, theta
+
+
+def _gp_of(gp_of, B, G):
+    if gp_of is None:
+        if B != G:
+            raise ValueError(f"gp_of is required when the number of pairs ({B}) differs from the number of GPs ({G})")
+        return None
+    gp = np.ascontiguousarray(gp_of, dtype=np.int32)
+    if gp.shape != (B,):
+        raise ValueError(f"gp_of must have shape ({B},), got {gp.shape}")
+    if gp.size and (gp.min() < 0 or gp.max() >= G):
+        raise ValueError("gp_of entry out of range")
+    return gp
+
+
+class OptimizerPool:
+    """The B L-BFGS-B state machines of a multi-start fit (``gpbo_optpool_*``; host memory only).  ``live()`` gives
+    the running pairs and their trial points, ``feed()`` takes their LML / gradient -- the loop of
+    ``gpbo_fit_host`` opened up so that ``sharding.fit_pairs`` can all-gather between the two."""
+
+    def __init__(self, bounds_log, starts, opts=None):
+        self._lib = load()
+        starts = _f64(np.atleast_2d(starts))
+        if starts.ndim != 2 or starts.shape[1] != 3:
+            raise ValueError("starts must have shape (B, 3)")
+        self.B = starts.shape[0]
+        bl = _f64(bounds_log, (3, 2))
+        o = None if opts is None else _f64(opts, (5,))
+        h = C.c_void_p()
+        _check(self._lib.gpbo_optpool_create(C.byref(h), self.B, _dp(bl), _dp(starts), _dp(o)), "gpbo_optpool_create")
+        self._h = h
+        self._idx = np.empty(self.B, dtype=np.int32)
+        self._theta = np.empty((self.B, 3))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.gpbo_optpool_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def live(self):
+        """-> (idx (n,) int32, theta (n, 3)) of the optimisers that still run (copies)."""
+        n = C.c_int()
+        _check(self._lib.gpbo_optpool_live(self._h, _ip(self._idx), _dp(self._theta), C.byref(n)), "gpbo_optpool_live")
+        return self._idx[:n.value].copy(), self._theta[:n.value].copy()
+
+    def feed(self, idx, lml, grad):
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        lml = _f64(lml)
+        grad = _f64(grad)
+        if lml.shape != idx.shape or grad.shape != (idx.size, 3):
+            raise ValueError("feed: shape mismatch")
+        _check(self._lib.gpbo_optpool_feed(self._h, int(idx.size), _ip(idx), _dp(lml), _dp(grad)), "gpbo_optpool_feed")
+
+    def result(self):
+        B = self.B
+        theta, fun = np.empty((B, 3)), np.empty(B)
+        nfev, nit, st = (np.empty(B, dtype=np.int32) for _ in range(3))
+        evals, rounds = C.c_longlong(), C.c_int()
+        _check(self._lib.gpbo_optpool_result(self._h, _dp(theta), _dp(fun), _ip(nfev), _ip(nit), _ip(st),
+                                             C.byref(evals), C.byref(rounds)), "gpbo_optpool_result")
+        return dict(theta=theta, fun=fun, nfev=nfev, nit=nit, status=st, evals=int(evals.value),
+                    rounds=int(rounds.value))
+
+
 class Context:
     """Owns one ``gpbo_ctx`` workspace handle on a CUDA device."""
 
@@ -115,6 +211,7 @@ class Context:
         _check(self._lib.gpbo_create(C.byref(h), int(device), int(max_workspace_bytes)), "gpbo_create")
         self._h = h
         self.device = int(device)
+        self.small_max = 224          # sizes up to this run on the in-shared small-matrix path (set_small_path)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -135,6 +232,41 @@ class Context:
     def set_kernel_family(self, twice_nu: int = 0):
         """0: RBF (the reference); 3 / 5: Matern nu = 3/2, 5/2.  Applies to all later calls on this context."""
         _check(self._lib.gpbo_set_kernel_family(self._h, int(twice_nu)), "gpbo_set_kernel_family")
+
+    @property
+    def stream(self) -> int:
+        """Address of the cudaStream_t the host-pointer entry points run on."""
+        p = C.c_void_p()
+        _check(self._lib.gpbo_get_stream(self._h, C.byref(p)), "gpbo_get_stream")
+        return int(p.value or 0)
+
+    def set_small_path(self, max_m: int = 224):
+        """Training sizes m <= max_m use the in-shared one-launch path (default 224); 0: always the blocked path."""
+        _check(self._lib.gpbo_set_small_path(self._h, int(max_m)), "gpbo_set_small_path")
+        self.small_max = min(int(max_m), 224)
+
+    def upload_problem(self, t, y):
+        """Keep (t, y): (G, m) resident in HBM for ``lml_grad_resident``."""
+        t, y = _problem(t, y)
+        _check(self._lib.gpbo_problem_upload_host(self._h, _dp(t), _dp(y), t.shape[0], t.shape[1]),
+               "gpbo_problem_upload_host")
+        self._resident = t.shape
+
+    def lml_grad_resident(self, theta, gp_of):
+        """LML + gradient of B pairs against the resident problem.  -> lml (B,), grad (B, 3), status (B,)."""
+        theta = _f64(np.atleast_2d(theta))
+        B = theta.shape[0]
+        if theta.ndim != 2 or (B and theta.shape[1] != 3):
+            raise ValueError("theta must have shape (B, 3)")
+        lml, grad, st = np.empty(B), np.empty((B, 3)), np.empty(B, dtype=np.int32)
+        if B == 0:
+            return lml, grad, st
+        if gp_of is None or getattr(self, "_resident", None) is None:
+            raise ValueError("lml_grad_resident needs gp_of and a problem uploaded with upload_problem()")
+        gp = _gp_of(gp_of, B, self._resident[0])
+        _check(self._lib.gpbo_lml_grad_resident_host(self._h, _dp(theta), _ip(gp), B, _dp(lml), _dp(grad), _ip(st)),
+               "gpbo_lml_grad_resident_host")
+        return lml, grad, st
 
     def wave_capacity(self, m: int) -> int:
         return int(self._lib.gpbo_wave_capacity(self._h, int(m)))
@@ -157,13 +289,10 @@ class Context:
     # -- host-pointer entry points ------------------------------------------------------
     def lml_grad(self, t, y, theta, gp_of=None, with_grad=True):
         """t, y: (G, m); theta: (B, 3); gp_of: (B,) int or None (B == G). -> lml (B,), grad (B,3), status (B,)."""
-        t, y = _f64(np.atleast_2d(t)), _f64(np.atleast_2d(y))
-        theta = _f64(np.atleast_2d(theta))
+        t, y, theta = _problem(t, y, theta)
         G, m = t.shape
         B = theta.shape[0]
-        if y.shape != t.shape or theta.shape[1] != 3:
-            raise ValueError("lml_grad: shape mismatch")
-        gp = None if gp_of is None else np.ascontiguousarray(gp_of, dtype=np.int32)
+        gp = _gp_of(gp_of, B, G)
         lml = np.empty(B)
         grad = np.empty((B, 3)) if with_grad else None
         st = np.empty(B, dtype=np.int32)
@@ -175,12 +304,11 @@ class Context:
         """Multi-start L-BFGS-B for all (GP, start) pairs in lock-step.
 
         bounds_log: (3, 2); starts: (B, 3).  Returns dict(theta, fun, nfev, nit, status, evals, rounds)."""
-        t, y = _f64(np.atleast_2d(t)), _f64(np.atleast_2d(y))
+        t, y, starts = _problem(t, y, starts)
         G, m = t.shape
-        starts = _f64(np.atleast_2d(starts))
         B = starts.shape[0]
         bl = _f64(bounds_log, (3, 2))
-        gp = None if gp_of is None else np.ascontiguousarray(gp_of, dtype=np.int32)
+        gp = _gp_of(gp_of, B, G)
         o = None if opts is None else _f64(opts, (5,))
         theta = np.empty((B, 3))
         fun = np.empty(B)
@@ -198,16 +326,17 @@ class Context:
     def _points(self, pts, G):
         pts = _f64(pts)
         if pts.ndim == 1:
+            if pts.shape[0] == 0:
+                raise ValueError("at least one evaluation point is required")
             return pts, 0, pts.shape[0]
-        if pts.shape[0] != G:
-            raise ValueError("per-GP evaluation points must have G rows")
+        if pts.ndim != 2 or pts.shape[0] != G or pts.shape[1] == 0:
+            raise ValueError("per-GP evaluation points must have shape (G, n)")
         return pts, pts.shape[1], pts.shape[1]
 
     def predict(self, t, y, theta, t_star, want_alpha=False):
         """Posterior mean and std at t_star ((n,) shared or (G, n)).  -> mean, std, alpha|None, status."""
-        t, y = _f64(np.atleast_2d(t)), _f64(np.atleast_2d(y))
+        t, y, theta = _problem(t, y, theta, n_theta=np.atleast_2d(t).shape[0])
         G, m = t.shape
-        theta = _f64(np.atleast_2d(theta))
         pts, stride, n = self._points(t_star, G)
         mean, std = np.empty((G, n)), np.empty((G, n))
         alpha = np.empty((G, m)) if want_alpha else None
@@ -218,9 +347,8 @@ class Context:
 
     def lstsq_moments(self, t, y, theta, t_est, want_cov=True):
         """state_estimate, ddt_estimate, ddt_covariance at t_est.  -> state, ddt, cov|None, status."""
-        t, y = _f64(np.atleast_2d(t)), _f64(np.atleast_2d(y))
+        t, y, theta = _problem(t, y, theta, n_theta=np.atleast_2d(t).shape[0])
         G, m = t.shape
-        theta = _f64(np.atleast_2d(theta))
         pts, stride, n = self._points(t_est, G)
         state, ddt = np.empty((G, n)), np.empty((G, n))
         cov = np.empty((G, n, n)) if want_cov else None
@@ -247,9 +375,8 @@ class Context:
     def lstsq_weights(self, t, y, theta, t_est, eta):
         """state, ddt, cov AND sqrtW in one call (the covariance never leaves HBM in between).
         -> state, ddt, cov, sqrtw, status, w_status, w_iters."""
-        t, y = _f64(np.atleast_2d(t)), _f64(np.atleast_2d(y))
+        t, y, theta = _problem(t, y, theta, n_theta=np.atleast_2d(t).shape[0])
         G, m = t.shape
-        theta = _f64(np.atleast_2d(theta))
         pts, stride, n = self._points(t_est, G)
         state, ddt = np.empty((G, n)), np.empty((G, n))
         cov, w = np.empty((G, n, n)), np.empty((G, n, n))

@@ -11,6 +11,7 @@
 
 #include "kernels_predict.cuh"
 #include "kernels_sqrtw.cuh"
+#include "kernels_small.cuh"
 #include "lbfgsb.h"
 
 using namespace gpbo;
@@ -48,6 +49,13 @@ struct DevBuf {
 
 struct ProfRec { int cls; cudaEvent_t e0, e1; };
 
+// Optimiser pool: every (GP, start) pair's L-BFGS-B state machine (host side, ~800 B each).
+struct OptPool {
+    std::vector<gpbo::Lbfgsb> opt;
+    long long evals = 0;
+    int rounds = 0;
+};
+
 }  // namespace
 
 struct gpbo_ctx {
@@ -58,6 +66,13 @@ struct gpbo_ctx {
     long long launches = 0;
     bool profiling = false;
     std::vector<ProfRec> recs;
+    std::vector<cudaEvent_t> ev_pool;   // recycled timing events: no cudaEventCreate inside a timed region
+    int sm_count = 0;
+    double* h_ns = nullptr; size_t h_ns_cap = 0;      // pinned residual read-back of the Newton-Schulz iteration
+    std::vector<cudaEvent_t> ns_events;
+    int small_max = SMALL_MAX;          // training sizes up to this run on the in-shared small-matrix path (0: never)
+    DevBuf sm_counter, sm_starts, sm_theta, sm_fun, sm_ints;
+    int G_res = 0, m_res = 0;           // shape of the problem resident in t_dev / y_dev (gpbo_problem_upload_host)
     double prof_ms[GPBO_NCLASS] = {0};
     long long prof_n[GPBO_NCLASS] = {0};
     // wave workspace
@@ -79,15 +94,18 @@ struct gpbo_ctx {
 
 namespace {
 
-enum { C_PREP = 0, C_DIAG, C_PANEL, C_TRSV, C_TRTRI, C_LAUUM, C_FINAL, C_CROSS, C_SCHUR, C_MEAN, C_ASM, C_SQRTW };
+enum { C_PREP = 0, C_DIAG, C_PANEL, C_TRSV, C_TRTRI, C_LAUUM, C_FINAL, C_CROSS, C_SCHUR, C_MEAN, C_ASM, C_SQRTW, C_SMALL };
 
 template <class F>
 inline void launch(gpbo_ctx* c, int cls, cudaStream_t s, F&& f) {
     if (c->profiling) {
         ProfRec r;
         r.cls = cls;
-        cudaEventCreate(&r.e0);
-        cudaEventCreate(&r.e1);
+        cudaEvent_t* ev[2] = {&r.e0, &r.e1};
+        for (cudaEvent_t* e : ev) {
+            if (c->ev_pool.empty()) cudaEventCreate(e);
+            else { *e = c->ev_pool.back(); c->ev_pool.pop_back(); }
+        }
         cudaEventRecord(r.e0, s);
         f();
         cudaEventRecord(r.e1, s);
@@ -116,21 +134,85 @@ int resolve_limit(gpbo_ctx* c) {
     return GPBO_OK;
 }
 
+int sm_count(gpbo_ctx* c) {
+    if (c->sm_count == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, c->device) != cudaSuccess || n <= 0) n = 148;
+        c->sm_count = n;
+    }
+    return c->sm_count;
+}
+
+// Pairs per wave for `want` pairs: as many as fit the workspace limit, then the `want` pairs are spread evenly over
+// the resulting number of waves (2048 pairs at a capacity of 1100 run as 1024 + 1024, not 1100 + 948), each wave a
+// multiple of the SM count when that costs no extra wave (kernels with one CTA per pair then fill whole rounds).
 int wave_capacity(gpbo_ctx* c, int m_pad, size_t extra_per_pair, size_t reserved, int want) {
     if (resolve_limit(c)) return -1;
     const size_t per = pair_bytes(m_pad) + extra_per_pair;
     if (c->limit <= reserved + per) return 0;
     size_t cap = (c->limit - reserved) / per;
-    if (cap > (size_t)want) cap = want;
-    else if (cap >= 148) cap = cap / 148 * 148;
-    return (int)cap;
+    if (cap >= (size_t)want) return want;
+    const size_t nw = ((size_t)want + cap - 1) / cap;
+    size_t even = ((size_t)want + nw - 1) / nw;
+    const size_t sms = (size_t)sm_count(c);
+    const size_t up = (even + sms - 1) / sms * sms;
+    if (up <= cap) even = up;
+    return (int)even;
 }
 
-int ensure_wave(gpbo_ctx* c, int m_pad, int cap) {
+// ---- workspace accounting ---------------------------------------------------------------------------------
+// Every operation sizes its waves as if it owned the whole workspace limit; the large buffers of OTHER operations
+// that are still cached (DevBuf never shrinks on its own) are released when the sum would exceed the limit, and a
+// buffer of this operation that is larger than now needed is given back if that is what it takes.
+struct Need { DevBuf* b; size_t bytes; };
+
+std::vector<DevBuf*> big_buffers(gpbo_ctx* c) {
+    return {&c->A, &c->D, &c->DT, &c->X, &c->pre, &c->nsY, &c->nsZ, &c->nsT, &c->nsTT, &c->nsYn, &c->nsZn,
+            &c->cov_dev, &c->w_dev, &c->wp_olhs};
+}
+
+int fit_buffers(gpbo_ctx* c, cudaStream_t s, const std::vector<Need>& needs) {
+    int rc = resolve_limit(c);
+    if (rc) return rc;
+    auto used = [&](const DevBuf* b) {
+        for (const Need& n : needs)
+            if (n.b == b) return true;
+        return false;
+    };
+    auto total = [&]() {
+        size_t tot = 0;
+        for (DevBuf* b : big_buffers(c))
+            if (!used(b)) tot += b->bytes;
+        for (const Need& n : needs) tot += std::max(n.b->bytes, n.bytes);
+        return tot;
+    };
+    if (total() > c->limit) {
+        CUDA_TRY(cudaStreamSynchronize(s));
+        for (DevBuf* b : big_buffers(c))
+            if (!used(b) && b->bytes) {
+                if (b == &c->w_dev) { c->w_G = 0; c->w_n = 0; }     // the resident sqrtW stack is gone
+                b->release();
+            }
+        if (total() > c->limit)
+            for (const Need& n : needs)
+                if (n.b->bytes > n.bytes) {
+                    if (n.b == &c->w_dev) { c->w_G = 0; c->w_n = 0; }
+                    n.b->release();
+                }
+    }
+    for (const Need& n : needs) CUDA_TRY(n.b->ensure(n.bytes));
+    return GPBO_OK;
+}
+
+// extra: further large buffers of the operation (prediction: X; fixed outputs kept alive: cov_dev, w_dev)
+int ensure_wave(gpbo_ctx* c, cudaStream_t s, int m_pad, int cap, std::vector<Need> extra = {}) {
     const size_t T = m_pad / TB, ntiles = T * (T + 1) / 2;
-    CUDA_TRY(c->A.ensure((size_t)cap * m_pad * m_pad * 8));
-    CUDA_TRY(c->D.ensure((size_t)cap * T * TB * TB * 8));
-    CUDA_TRY(c->DT.ensure((size_t)cap * T * TB * TB * 8));
+    extra.push_back({&c->A, (size_t)cap * m_pad * m_pad * 8});
+    extra.push_back({&c->D, (size_t)cap * T * TB * TB * 8});
+    extra.push_back({&c->DT, (size_t)cap * T * TB * TB * 8});
+    extra.push_back({&c->pre, c->pre.bytes});          // split-K scratch: sized on demand, kept
+    int rc0 = fit_buffers(c, s, extra);
+    if (rc0) return rc0;
     CUDA_TRY(c->ts.ensure((size_t)cap * m_pad * 8));
     CUDA_TRY(c->z.ensure((size_t)cap * m_pad * 8));
     CUDA_TRY(c->alpha.ensure((size_t)cap * m_pad * 8));
@@ -191,15 +273,10 @@ int set_kernel_attrs() {
 // Split-K policy: with fewer than ~one CTA per SM in a launch whose tiles run a k-loop of nk_max slices, the loop
 // is cut into up to 16 chunks of >= 4 slices computed by separate CTAs (splitk_partial_kernel) first.
 // Returns a PreAcc with buf == nullptr when the fused kernels should run their own loop.
-int g_sm_count = 0;   // one process drives one GPU model: the SM count is the same on every device of a box
 int plan_split(gpbo_ctx* c, cudaStream_t s, const MatArgs& a, int mode, int idx, int nb, int ntile, int nk_max,
                const double* X, long x_stride, PreAcc* out) {
     out->buf = nullptr; out->nsplit = 1; out->chunk = nk_max;
-    if (g_sm_count == 0) {
-        cudaDeviceProp prop;
-        CUDA_TRY(cudaGetDeviceProperties(&prop, c->device));
-        g_sm_count = prop.multiProcessorCount;
-    }
+    const int g_sm_count = sm_count(c);
     const long units = (long)nb * ntile;
     if (units <= 0 || nk_max < 16) return GPBO_OK;
     // tuning knobs (defaults measured on B200): at most SPLIT_MAX chunks of at least SPLIT_MIN slices
@@ -295,6 +372,126 @@ int eval_wave(gpbo_ctx* c, cudaStream_t s, const double* t_dev, const double* yp
     return GPBO_OK;
 }
 
+// ---- small-matrix path (kernels_small.cuh) ---------------------------------------------------------------
+bool small_path_ok(const gpbo_ctx* c, int m) { return m <= c->small_max && m <= SMALL_MAX; }
+
+bool g_small_attr_done[64] = {false};
+template <int NT, int FAM>
+int small_attrs_one() {
+    CUDA_TRY(cudaFuncSetAttribute(small_lml_grad_kernel<NT, FAM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)small_smem_bytes(NT == 64 ? 64 : SMALL_MAX)));
+    CUDA_TRY(cudaFuncSetAttribute(small_fit_kernel<NT, FAM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)small_smem_bytes(NT == 64 ? 64 : SMALL_MAX)));
+    return GPBO_OK;
+}
+int set_small_attrs() {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && g_small_attr_done[dev]) return GPBO_OK;
+    int rc;
+    if ((rc = small_attrs_one<64, 0>()) || (rc = small_attrs_one<64, 3>()) || (rc = small_attrs_one<64, 5>()) ||
+        (rc = small_attrs_one<256, 0>()) || (rc = small_attrs_one<256, 3>()) || (rc = small_attrs_one<256, 5>()))
+        return rc;
+    if (dev >= 0 && dev < 64) g_small_attr_done[dev] = true;
+    return GPBO_OK;
+}
+
+// CTAs that can be resident at once for the small kernels (persistent grids are sized to this)
+template <class K>
+int small_resident(gpbo_ctx* c, K kernel, int nt, size_t smem) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, nt, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    return per_sm * sm_count(c);
+}
+
+// LML (+ gradient) of B pairs, one CTA per pair, one launch.  All pointers device.
+int small_lml_grad_device(gpbo_ctx* c, cudaStream_t s, const double* t, const double* y, int m, const double* theta,
+                          const int* gp_of, int B, double* lml, double* grad, int* status) {
+    int rc = set_small_attrs();
+    if (rc) return rc;
+    SmallProblem pr{t, y, m, small_pad(m)};
+    const size_t smem = small_smem_bytes(pr.n);
+    const int fam = c->family;
+    launch(c, C_SMALL, s, [&] {
+#define GPBO_SMALL_LML(NT, F)                                                                                    \
+    small_lml_grad_kernel<NT, F><<<std::min(B, 8 * small_resident(c, small_lml_grad_kernel<NT, F>, NT, smem)), NT, \
+                                   smem, s>>>(pr, theta, gp_of, B, lml, grad, status)
+        if (pr.n <= 64) {
+            if (fam == 0) GPBO_SMALL_LML(64, 0); else if (fam == 3) GPBO_SMALL_LML(64, 3); else GPBO_SMALL_LML(64, 5);
+        } else {
+            if (fam == 0) GPBO_SMALL_LML(256, 0); else if (fam == 3) GPBO_SMALL_LML(256, 3); else GPBO_SMALL_LML(256, 5);
+        }
+#undef GPBO_SMALL_LML
+    });
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return GPBO_OK;
+}
+
+// The whole multi-start fit as one persistent kernel.  t_dev / y_dev hold the problem; starts / gp_of / outputs HOST.
+int small_fit_device(gpbo_ctx* c, cudaStream_t s, int G, int m, const double* bounds_log, const double* starts,
+                     const int* gp_of, int B, const double* opts, double* theta_opt, double* fun, int* nfev, int* nit,
+                     int* opt_status, long long* total_evals, int* rounds) {
+    (void)G;
+    int rc = set_small_attrs();
+    if (rc) return rc;
+    LbOptions o;
+    if (opts) {
+        o.factr = opts[0]; o.pgtol = opts[1]; o.maxiter = (int)opts[2]; o.maxfun = (int)opts[3]; o.maxls = (int)opts[4];
+    }
+    SmallBox box;
+    for (int i = 0; i < 3; ++i) { box.lo[i] = bounds_log[2 * i]; box.hi[i] = bounds_log[2 * i + 1]; }
+    CUDA_TRY(c->sm_counter.ensure(4));
+    CUDA_TRY(c->sm_starts.ensure((size_t)B * 24));
+    CUDA_TRY(c->sm_theta.ensure((size_t)B * 24));
+    CUDA_TRY(c->sm_fun.ensure((size_t)B * 8));
+    CUDA_TRY(c->sm_ints.ensure((size_t)B * 16));
+    CUDA_TRY(cudaMemsetAsync(c->sm_counter.p, 0, 4, s));
+    CUDA_TRY(cudaMemcpyAsync(c->sm_starts.p, starts, (size_t)B * 24, cudaMemcpyHostToDevice, s));
+    std::vector<int> gp(B);
+    for (int b = 0; b < B; ++b) gp[b] = gp_of ? gp_of[b] : b;
+    int* d_gp = c->sm_ints.as<int>();
+    int* d_nfev = d_gp + B;
+    int* d_nit = d_nfev + B;
+    int* d_st = d_nit + B;
+    CUDA_TRY(cudaMemcpyAsync(d_gp, gp.data(), (size_t)B * 4, cudaMemcpyHostToDevice, s));
+    SmallProblem pr{c->t_dev.as<double>(), c->y_dev.as<double>(), m, small_pad(m)};
+    const size_t smem = small_smem_bytes(pr.n);
+    const int fam = c->family;
+    launch(c, C_SMALL, s, [&] {
+#define GPBO_SMALL_FIT(NT, F)                                                                                     \
+    small_fit_kernel<NT, F><<<std::min(B, small_resident(c, small_fit_kernel<NT, F>, NT, smem)), NT, smem, s>>>(  \
+        pr, c->sm_starts.as<double>(), d_gp, B, box, o, c->sm_counter.as<int>(), c->sm_theta.as<double>(),        \
+        c->sm_fun.as<double>(), d_nfev, d_nit, d_st)
+        if (pr.n <= 64) {
+            if (fam == 0) GPBO_SMALL_FIT(64, 0); else if (fam == 3) GPBO_SMALL_FIT(64, 3); else GPBO_SMALL_FIT(64, 5);
+        } else {
+            if (fam == 0) GPBO_SMALL_FIT(256, 0); else if (fam == 3) GPBO_SMALL_FIT(256, 3); else GPBO_SMALL_FIT(256, 5);
+        }
+#undef GPBO_SMALL_FIT
+    });
+    CUDA_TRY(cudaGetLastError());
+    std::vector<int> h_nfev(B), h_nit(B), h_st(B);
+    CUDA_TRY(cudaMemcpyAsync(theta_opt, c->sm_theta.p, (size_t)B * 24, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(fun, c->sm_fun.p, (size_t)B * 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(h_nfev.data(), d_nfev, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(h_nit.data(), d_nit, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(h_st.data(), d_st, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    long long ev = 0;
+    int longest = 0;
+    for (int b = 0; b < B; ++b) {
+        ev += h_nfev[b];
+        longest = std::max(longest, h_nfev[b]);
+        if (nfev) nfev[b] = h_nfev[b];
+        if (nit) nit[b] = h_nit[b];
+        if (opt_status) opt_status[b] = h_st[b];
+    }
+    if (total_evals) *total_evals = ev;
+    if (rounds) *rounds = longest;       // no lock-step here: the longest chain of evaluations of any pair
+    return GPBO_OK;
+}
+
 int make_ypad(gpbo_ctx* c, cudaStream_t s, const double* y_dev, int G, int m, int m_pad) {
     CUDA_TRY(c->ypad.ensure((size_t)G * m_pad * 8));
     launch(c, C_PREP, s, [&] { pad_rows_kernel<<<G, 256, 0, s>>>(y_dev, m, m_pad, c->ypad.as<double>()); });
@@ -308,13 +505,14 @@ int lml_grad_device(gpbo_ctx* c, cudaStream_t s, const double* t, const double* 
     if (B == 0) return GPBO_OK;
     if (!gp_of) return fail(GPBO_EINVAL, "lml_grad: internal: gp_of must be materialised");
     CUDA_TRY(cudaSetDevice(c->device));
+    if (small_path_ok(c, m)) return small_lml_grad_device(c, s, t, y, m, theta, gp_of, B, lml, grad, status);
     int rc = set_kernel_attrs();
     if (rc) return rc;
     const int m_pad = pad_to_tile(m);
     const size_t reserved = (size_t)G * m_pad * 8 + (1 << 20);
     const int cap = wave_capacity(c, m_pad, 0, reserved, B);
     if (cap <= 0) return fail(GPBO_ENOMEM, "lml_grad: one pair does not fit the workspace limit");
-    rc = ensure_wave(c, m_pad, cap);
+    rc = ensure_wave(c, s, m_pad, cap);
     if (rc) return rc;
     rc = make_ypad(c, s, y, G, m, m_pad);
     if (rc) return rc;
@@ -340,35 +538,39 @@ int sqrtw_device(gpbo_ctx* c, cudaStream_t s, const double* cov, int G, int n, d
     const size_t mat = (size_t)ld * ld * 8;
     const int nfull = T * T;
     const size_t per = 6 * mat + (size_t)nfull * 8 + 64;
-    // memory still free + what the Newton-Schulz buffers already hold; the factorisation waves are dropped
-    // if that is what it takes to fit one matrix
-    auto avail = [&]() -> size_t {
-        size_t fr = 0, tot = 0;
-        if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) return 0;
-        const size_t held = c->nsY.bytes + c->nsZ.bytes + c->nsT.bytes + c->nsTT.bytes + c->nsYn.bytes + c->nsZn.bytes;
-        return (size_t)(0.9 * (double)fr) + held;
-    };
-    size_t av = avail();
-    if (av < (size_t)std::min(G, 8) * per) {
-        CUDA_TRY(cudaStreamSynchronize(s));
-        c->A.release(); c->X.release(); c->D.release(); c->DT.release();
-        av = avail();
+    // the input / output stacks count against the limit when they are the library's own staging buffers
+    const bool own_io = (cov == c->cov_dev.as<double>()) && (out == c->w_dev.as<double>());
+    const size_t fixed = own_io ? c->cov_dev.bytes + c->w_dev.bytes : 0;
+    if (c->limit < fixed + per) return fail(GPBO_ENOMEM, "sqrtw: one matrix does not fit the workspace limit");
+    int cap = (int)std::min<size_t>((size_t)G, (c->limit - fixed) / per);
+    {
+        std::vector<Need> needs = {{&c->nsY, cap * mat}, {&c->nsZ, cap * mat}, {&c->nsT, cap * mat},
+                                   {&c->nsTT, cap * mat}, {&c->nsYn, cap * mat}, {&c->nsZn, cap * mat}};
+        if (own_io) { needs.push_back({&c->cov_dev, c->cov_dev.bytes}); needs.push_back({&c->w_dev, c->w_dev.bytes}); }
+        rc = fit_buffers(c, s, needs);
+        if (rc) return rc;
     }
-    if (av < per) return fail(GPBO_ENOMEM, "sqrtw: one matrix does not fit in device memory");
-    int cap = (int)std::min<size_t>((size_t)G, av / per);
-    CUDA_TRY(c->nsY.ensure(cap * mat));
-    CUDA_TRY(c->nsZ.ensure(cap * mat));
-    CUDA_TRY(c->nsT.ensure(cap * mat));
-    CUDA_TRY(c->nsTT.ensure(cap * mat));
-    CUDA_TRY(c->nsYn.ensure(cap * mat));
-    CUDA_TRY(c->nsZn.ensure(cap * mat));
     CUDA_TRY(c->nsPart.ensure((size_t)cap * nfull * 8));
     CUDA_TRY(c->nsNorm.ensure((size_t)cap * 8));
     CUDA_TRY(c->nsResid.ensure((size_t)cap * 8));
     const int maxit = 90;
     const bool debug_ns = std::getenv("GPBO_DEBUG_NS") != nullptr;
-    std::vector<double> resid(cap), prev(cap);
+    const bool plain_ns = std::getenv("GPBO_NS_PLAIN") != nullptr;       // unscaled iteration (for comparison runs)
+    std::vector<double> prev(cap), lk(cap);
     std::vector<char> done(cap);
+    // residual read-back: pinned, one slot per iteration, checked ONE iteration late so that the host never drains
+    // the GPU queue (iteration k+1's first product is already enqueued when iteration k's residual is looked at)
+    if (c->h_ns_cap < (size_t)maxit * cap) {
+        if (c->h_ns) cudaFreeHost(c->h_ns);
+        c->h_ns = nullptr; c->h_ns_cap = 0;
+        CUDA_TRY(cudaMallocHost(&c->h_ns, (size_t)(maxit + 1) * cap * 8));
+        c->h_ns_cap = (size_t)maxit * cap;
+    }
+    while ((int)c->ns_events.size() < maxit + 1) {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->ns_events.push_back(e);
+    }
     for (int w0 = 0; w0 < G; w0 += cap) {
         const int nb = std::min(cap, G - w0);
         const double* Cw = cov + (size_t)w0 * n * n;
@@ -380,12 +582,21 @@ int sqrtw_device(gpbo_ctx* c, cudaStream_t s, const double* cov, int G, int n, d
         CUDA_TRY(cudaMemsetAsync(norm, 0, (size_t)nb * 8, s));
         launch(c, C_SQRTW, s, [&] { ns_norm_kernel<<<dim3((n + 7) / 8, nb), NTHR, 0, s>>>(Cw, n, eta, norm); });
         launch(c, C_SQRTW, s, [&] { ns_init_kernel<<<dim3(ld, nb), NTHR, 0, s>>>(Cw, n, eta, norm, a); });
+        // scaling bound l_0 = sqrt(eta / s) per matrix; the batch is stepped with the smallest bound (safe for all)
+        double* h_norm = c->h_ns + (size_t)maxit * cap;
+        CUDA_TRY(cudaMemcpyAsync(h_norm, norm, (size_t)nb * 8, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        double l = 1.0;
+        for (int p = 0; p < nb; ++p) {
+            const double sp = h_norm[p];
+            const double lp = (eta > 0.0 && sp > 0.0 && std::isfinite(sp)) ? std::sqrt(std::min(1.0, eta / sp)) : 1e-8;
+            l = std::min(l, std::max(lp, 1e-8));
+        }
+        if (plain_ns) l = 1.0;
         for (int p = 0; p < nb; ++p) { done[p] = 0; prev[p] = HUGE_VAL; if (status) status[w0 + p] = 0; if (iters) iters[w0 + p] = maxit; }
-        for (int it = 0; it < maxit; ++it) {
-            launch(c, C_SQRTW, s, [&] { ns_gemm_kernel<<<dim3(nb * nfull, 1), NTHR, MAIN_SMEM, s>>>(a, nfull, 0); });
-            launch(c, C_SQRTW, s, [&] { ns_resid_kernel<<<nb, NTHR, 0, s>>>(a.part, nfull, c->nsResid.as<double>()); });
-            CUDA_TRY(cudaMemcpyAsync(resid.data(), c->nsResid.p, (size_t)nb * 8, cudaMemcpyDeviceToHost, s));
-            CUDA_TRY(cudaStreamSynchronize(s));
+        // convergence bookkeeping for the residual of iteration `it`; returns whether every matrix is finished
+        auto judge = [&](int it) {
+            const double* resid = c->h_ns + (size_t)it * cap;
             bool all_done = true;
             if (debug_ns) std::fprintf(stderr, "[gpbo sqrtw] it %d r0 %.6e\n", it, std::sqrt(resid[0]));
             for (int p = 0; p < nb; ++p) {
@@ -402,8 +613,26 @@ int sqrtw_device(gpbo_ctx* c, cudaStream_t s, const double* cov, int G, int n, d
                 prev[p] = r;
                 if (!done[p]) all_done = false;
             }
-            if (all_done) break;
-            launch(c, C_SQRTW, s, [&] { ns_gemm_kernel<<<dim3(nb * ntiles, 2), NTHR, MAIN_SMEM, s>>>(a, ntiles, 1); });
+            return all_done;
+        };
+        for (int it = 0; it < maxit; ++it) {
+            launch(c, C_SQRTW, s, [&] { ns_gemm_kernel<<<dim3(nb * nfull, 1), NTHR, MAIN_SMEM, s>>>(a, nfull, 0, 0.0, 0.0); });
+            launch(c, C_SQRTW, s, [&] { ns_resid_kernel<<<nb, NTHR, 0, s>>>(a.part, nfull, c->nsResid.as<double>()); });
+            CUDA_TRY(cudaMemcpyAsync(c->h_ns + (size_t)it * cap, c->nsResid.p, (size_t)nb * 8, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(cudaEventRecord(c->ns_events[it], s));
+            if (it >= 1) {
+                CUDA_TRY(cudaEventSynchronize(c->ns_events[it - 1]));
+                if (judge(it - 1)) break;          // Y, Z already hold the (further improved) iterate `it`
+            }
+            if (it == maxit - 1) {
+                CUDA_TRY(cudaEventSynchronize(c->ns_events[it]));
+                judge(it);
+                break;
+            }
+            const double mu = std::sqrt(3.0 / (1.0 + l + l * l));
+            const double ca = 1.5 * mu, cb = 0.5 * mu * mu * mu;
+            l = std::min(1.0, 0.5 * mu * l * (3.0 - mu * mu * l * l));
+            launch(c, C_SQRTW, s, [&] { ns_gemm_kernel<<<dim3(nb * ntiles, 2), NTHR, MAIN_SMEM, s>>>(a, ntiles, 1, ca, cb); });
             std::swap(a.Y, a.Yn);
             std::swap(a.Z, a.Zn);
         }
@@ -448,9 +677,13 @@ int gpbo_destroy(gpbo_ctx* c) {
                       &c->t_dev, &c->y_dev, &c->ypad, &c->theta_dev, &c->gpof_dev, &c->lml_dev, &c->grad_dev, &c->st_dev,
                       &c->X, &c->trow, &c->tsrc, &c->out1, &c->out2, &c->cov_dev,
                       &c->nsY, &c->nsZ, &c->nsT, &c->nsTT, &c->nsYn, &c->nsZn, &c->nsPart, &c->nsNorm, &c->nsResid, &c->w_dev,
-                      &c->pre, &c->wp_lhs, &c->wp_rhs, &c->wp_olhs, &c->wp_orhs};
+                      &c->pre, &c->wp_lhs, &c->wp_rhs, &c->wp_olhs, &c->wp_orhs,
+                      &c->sm_counter, &c->sm_starts, &c->sm_theta, &c->sm_fun, &c->sm_ints};
     for (DevBuf* b : bufs) b->release();
     for (auto& r : c->recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->ns_events) cudaEventDestroy(e);
+    if (c->h_ns) cudaFreeHost(c->h_ns);
     if (c->h_theta) cudaFreeHost(c->h_theta);
     if (c->h_lml) cudaFreeHost(c->h_lml);
     if (c->h_grad) cudaFreeHost(c->h_grad);
@@ -470,6 +703,18 @@ int gpbo_set_kernel_family(gpbo_ctx* c, int twice_nu) {
     return GPBO_OK;
 }
 
+int gpbo_get_stream(gpbo_ctx* c, void** stream) {
+    if (!c || !stream) return fail(GPBO_EINVAL, "get_stream: bad argument");
+    *stream = static_cast<void*>(c->stream);
+    return GPBO_OK;
+}
+
+int gpbo_set_small_path(gpbo_ctx* c, int max_m) {
+    if (!c || max_m < 0) return fail(GPBO_EINVAL, "set_small_path: bad argument");
+    c->small_max = std::min(max_m, (int)SMALL_MAX);
+    return GPBO_OK;
+}
+
 int gpbo_wave_capacity(gpbo_ctx* c, int m) {
     if (!c || m <= 0) return fail(GPBO_EINVAL, "wave_capacity: bad argument");
     if (cudaSetDevice(c->device) != cudaSuccess) return fail(GPBO_ECUDA, "cudaSetDevice failed");
@@ -478,7 +723,7 @@ int gpbo_wave_capacity(gpbo_ctx* c, int m) {
 
 int gpbo_profile_enable(gpbo_ctx* c, int on) {
     if (!c) return fail(GPBO_EINVAL, "profile_enable: ctx is NULL");
-    for (auto& r : c->recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    for (auto& r : c->recs) { c->ev_pool.push_back(r.e0); c->ev_pool.push_back(r.e1); }
     c->recs.clear();
     for (int i = 0; i < GPBO_NCLASS; ++i) { c->prof_ms[i] = 0; c->prof_n[i] = 0; }
     c->profiling = on != 0;
@@ -494,8 +739,8 @@ int gpbo_profile_get(gpbo_ctx* c, double* ms, long long* launches) {
         cudaEventElapsedTime(&f, r.e0, r.e1);
         c->prof_ms[r.cls] += f;
         c->prof_n[r.cls] += 1;
-        cudaEventDestroy(r.e0);
-        cudaEventDestroy(r.e1);
+        c->ev_pool.push_back(r.e0);
+        c->ev_pool.push_back(r.e1);
     }
     c->recs.clear();
     for (int i = 0; i < GPBO_NCLASS; ++i) { ms[i] = c->prof_ms[i]; launches[i] = c->prof_n[i]; }
@@ -549,12 +794,15 @@ int gpbo_lml_grad(gpbo_ctx* c, const double* t, const double* y, int G, int m, c
     if (!c) return fail(GPBO_EINVAL, "lml_grad: ctx is NULL");
     if (!gp_of && B != G) return fail(GPBO_EINVAL, "lml_grad: gp_of is NULL but B != G");
     if (!gp_of) {
-        // identity map: materialise it so waves can be sliced uniformly
+        // identity map: materialise it so waves can be sliced uniformly (copied on the caller's stream, so it is
+        // ordered against earlier work of a non-blocking stream; the host vector outlives the copy)
         CUDA_TRY(cudaSetDevice(c->device));
         std::vector<int> id(B);
         for (int i = 0; i < B; ++i) id[i] = i;
         CUDA_TRY(c->gpof_dev.ensure((size_t)B * 4));
-        CUDA_TRY(cudaMemcpy(c->gpof_dev.p, id.data(), (size_t)B * 4, cudaMemcpyHostToDevice));
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        CUDA_TRY(cudaMemcpyAsync(c->gpof_dev.p, id.data(), (size_t)B * 4, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
         gp_of = c->gpof_dev.as<int>();
     }
     return lml_grad_device(c, static_cast<cudaStream_t>(stream), t, y, G, m, theta, gp_of, B, lml, grad, status);
@@ -571,6 +819,7 @@ static bool all_finite(const double* v, size_t n) {
 static int upload_problem(gpbo_ctx* c, cudaStream_t s, const double* t, const double* y, int G, int m) {
     if (!all_finite(t, (size_t)G * m) || !all_finite(y, (size_t)G * m))
         return fail(GPBO_EINVAL, "input contains NaN or infinity (t or y)");
+    c->G_res = 0; c->m_res = 0;       // t_dev / y_dev are about to change: a resident problem is no longer valid
     CUDA_TRY(c->t_dev.ensure((size_t)G * m * 8));
     CUDA_TRY(c->y_dev.ensure((size_t)G * m * 8));
     CUDA_TRY(cudaMemcpyAsync(c->t_dev.p, t, (size_t)G * m * 8, cudaMemcpyHostToDevice, s));
@@ -620,23 +869,37 @@ int gpbo_lml_grad_host(gpbo_ctx* c, const double* t, const double* y, int G, int
     return GPBO_OK;
 }
 
-int gpbo_fit_host(gpbo_ctx* c, const double* t, const double* y, int G, int m, const double* bounds_log,
-                  const double* starts, const int* gp_of, int B, const double* opts, double* theta_opt, double* fun,
-                  int* nfev, int* nit, int* opt_status, long long* total_evals, int* rounds) {
-    if (!c || !t || !y || !bounds_log || !starts || !theta_opt || !fun || G <= 0 || m <= 0 || B <= 0)
-        return fail(GPBO_EINVAL, "fit_host: bad argument");
-    if (!gp_of && B != G) return fail(GPBO_EINVAL, "fit_host: gp_of is NULL but B != G");
+static int pool_init(OptPool& pool, int B, const double* bounds_log, const double* starts, const double* opts) {
     for (int i = 0; i < 3; ++i)
-        if (!(bounds_log[2 * i] <= bounds_log[2 * i + 1])) return fail(GPBO_EINVAL, "fit_host: empty bound interval");
-    if (gp_of)
-        for (int b = 0; b < B; ++b)
-            if (gp_of[b] < 0 || gp_of[b] >= G) return fail(GPBO_EINVAL, "fit_host: gp_of entry out of range");
-    CUDA_TRY(cudaSetDevice(c->device));
-    cudaStream_t s = c->stream;
-    int rc = upload_problem(c, s, t, y, G, m);
-    if (rc) return rc;
+        if (!(bounds_log[2 * i] <= bounds_log[2 * i + 1])) return fail(GPBO_EINVAL, "empty bound interval");
+    LbOptions o;
+    if (opts) {
+        o.factr = opts[0]; o.pgtol = opts[1]; o.maxiter = (int)opts[2]; o.maxfun = (int)opts[3]; o.maxls = (int)opts[4];
+    }
+    double lo[3] = {bounds_log[0], bounds_log[2], bounds_log[4]};
+    double hi[3] = {bounds_log[1], bounds_log[3], bounds_log[5]};
+    pool.opt.assign(B, Lbfgsb());
+    for (int b = 0; b < B; ++b) pool.opt[b].init(starts + 3 * (size_t)b, lo, hi, o);
+    pool.evals = 0;
+    pool.rounds = 0;
+    return GPBO_OK;
+}
+
+static void pool_result(const OptPool& pool, double* theta_opt, double* fun, int* nfev, int* nit, int* opt_status) {
+    const int B = (int)pool.opt.size();
+    for (int b = 0; b < B; ++b) {
+        const Lbfgsb& o = pool.opt[b];
+        o.current_best(theta_opt + 3 * (size_t)b, fun + b);
+        if (nfev) nfev[b] = o.nfev;
+        if (nit) nit[b] = o.nit;
+        if (opt_status) opt_status[b] = o.status;
+    }
+}
+
+static int ensure_round_buffers(gpbo_ctx* c, int B) {
     if (c->h_cap < (size_t)B) {
         if (c->h_theta) { cudaFreeHost(c->h_theta); cudaFreeHost(c->h_lml); cudaFreeHost(c->h_grad); cudaFreeHost(c->h_gpof); }
+        c->h_theta = nullptr; c->h_cap = 0;
         CUDA_TRY(cudaMallocHost(&c->h_theta, (size_t)B * 24));
         CUDA_TRY(cudaMallocHost(&c->h_lml, (size_t)B * 8));
         CUDA_TRY(cudaMallocHost(&c->h_grad, (size_t)B * 24));
@@ -647,55 +910,166 @@ int gpbo_fit_host(gpbo_ctx* c, const double* t, const double* y, int G, int m, c
     CUDA_TRY(c->gpof_dev.ensure((size_t)B * 4));
     CUDA_TRY(c->lml_dev.ensure((size_t)B * 8));
     CUDA_TRY(c->grad_dev.ensure((size_t)B * 24));
+    CUDA_TRY(c->st_dev.ensure((size_t)B * 4));
+    return GPBO_OK;
+}
 
-    LbOptions o;
-    if (opts) {
-        o.factr = opts[0]; o.pgtol = opts[1]; o.maxiter = (int)opts[2]; o.maxfun = (int)opts[3]; o.maxls = (int)opts[4];
+// LML + gradient of n pairs whose theta / gp_of sit in the pinned staging buffers, for the problem resident in
+// t_dev / y_dev; results land in h_lml / h_grad.  One lock-step round of the optimiser.
+static int eval_round(gpbo_ctx* c, cudaStream_t s, int G, int m, int n) {
+    CUDA_TRY(cudaMemcpyAsync(c->theta_dev.p, c->h_theta, (size_t)n * 24, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(c->gpof_dev.p, c->h_gpof, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    int rc = lml_grad_device(c, s, c->t_dev.as<double>(), c->y_dev.as<double>(), G, m, c->theta_dev.as<double>(),
+                             c->gpof_dev.as<int>(), n, c->lml_dev.as<double>(), c->grad_dev.as<double>(), nullptr);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c->h_lml, c->lml_dev.p, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(c->h_grad, c->grad_dev.p, (size_t)n * 24, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return GPBO_OK;
+}
+
+int gpbo_fit_host(gpbo_ctx* c, const double* t, const double* y, int G, int m, const double* bounds_log,
+                  const double* starts, const int* gp_of, int B, const double* opts, double* theta_opt, double* fun,
+                  int* nfev, int* nit, int* opt_status, long long* total_evals, int* rounds) {
+    if (!c || !t || !y || !bounds_log || !starts || !theta_opt || !fun || G <= 0 || m <= 0 || B <= 0)
+        return fail(GPBO_EINVAL, "fit_host: bad argument");
+    if (!gp_of && B != G) return fail(GPBO_EINVAL, "fit_host: gp_of is NULL but B != G");
+    if (gp_of)
+        for (int b = 0; b < B; ++b)
+            if (gp_of[b] < 0 || gp_of[b] >= G) return fail(GPBO_EINVAL, "fit_host: gp_of entry out of range");
+    OptPool pool;
+    int rc = pool_init(pool, B, bounds_log, starts, opts);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    rc = upload_problem(c, s, t, y, G, m);
+    if (rc) return rc;
+    if (small_path_ok(c, m)) {
+        // reference-size problems: the whole multi-start fit runs as ONE persistent kernel, optimiser on device
+        rc = small_fit_device(c, s, G, m, bounds_log, starts, gp_of, B, opts, theta_opt, fun, nfev, nit, opt_status,
+                              total_evals, rounds);
+        return rc;
     }
-    double lo[3] = {bounds_log[0], bounds_log[2], bounds_log[4]};
-    double hi[3] = {bounds_log[1], bounds_log[3], bounds_log[5]};
-    std::vector<Lbfgsb> opt(B);
-    for (int b = 0; b < B; ++b) opt[b].init(starts + 3 * (size_t)b, lo, hi, o);
+    rc = ensure_round_buffers(c, B);
+    if (rc) return rc;
     std::vector<int> live;
     live.reserve(B);
-    long long evals = 0;
-    int nround = 0;
     for (;;) {
         live.clear();
         for (int b = 0; b < B; ++b)
-            if (opt[b].running()) live.push_back(b);
+            if (pool.opt[b].running()) live.push_back(b);
         if (live.empty()) break;
         const int n = (int)live.size();
         for (int k = 0; k < n; ++k) {
             const int b = live[k];
-            c->h_theta[3 * k] = opt[b].x[0]; c->h_theta[3 * k + 1] = opt[b].x[1]; c->h_theta[3 * k + 2] = opt[b].x[2];
+            c->h_theta[3 * k] = pool.opt[b].x[0]; c->h_theta[3 * k + 1] = pool.opt[b].x[1]; c->h_theta[3 * k + 2] = pool.opt[b].x[2];
             c->h_gpof[k] = gp_of ? gp_of[b] : b;
         }
-        CUDA_TRY(cudaMemcpyAsync(c->theta_dev.p, c->h_theta, (size_t)n * 24, cudaMemcpyHostToDevice, s));
-        CUDA_TRY(cudaMemcpyAsync(c->gpof_dev.p, c->h_gpof, (size_t)n * 4, cudaMemcpyHostToDevice, s));
-        rc = lml_grad_device(c, s, c->t_dev.as<double>(), c->y_dev.as<double>(), G, m, c->theta_dev.as<double>(),
-                             c->gpof_dev.as<int>(), n, c->lml_dev.as<double>(), c->grad_dev.as<double>(), nullptr);
+        rc = eval_round(c, s, G, m, n);
         if (rc) return rc;
-        CUDA_TRY(cudaMemcpyAsync(c->h_lml, c->lml_dev.p, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(cudaMemcpyAsync(c->h_grad, c->grad_dev.p, (size_t)n * 24, cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(cudaStreamSynchronize(s));
         for (int k = 0; k < n; ++k) {
             const int b = live[k];
             double gneg[3] = {-c->h_grad[3 * k], -c->h_grad[3 * k + 1], -c->h_grad[3 * k + 2]};
-            opt[b].feed(-c->h_lml[k], gneg);   // obj_func = (-lml, -grad), _gpr.py:300-307
+            pool.opt[b].feed(-c->h_lml[k], gneg);   // obj_func = (-lml, -grad), _gpr.py:300-307
         }
-        evals += n;
-        nround += 1;
+        pool.evals += n;
+        pool.rounds += 1;
     }
+    pool_result(pool, theta_opt, fun, nfev, nit, opt_status);
+    if (total_evals) *total_evals = pool.evals;
+    if (rounds) *rounds = pool.rounds;
+    return GPBO_OK;
+}
+
+// ---- optimiser pool + resident problem: the pieces of gpbo_fit_host, exposed so that a multi-GPU driver can
+// interleave one all-gather per lock-step round (sharding.py) ------------------------------------------------
+struct gpbo_optpool { OptPool pool; };
+
+int gpbo_optpool_create(gpbo_optpool** out, int B, const double* bounds_log, const double* starts, const double* opts) {
+    if (!out || B <= 0 || !bounds_log || !starts) return fail(GPBO_EINVAL, "optpool_create: bad argument");
+    gpbo_optpool* h = new gpbo_optpool();
+    int rc = pool_init(h->pool, B, bounds_log, starts, opts);
+    if (rc) { delete h; return rc; }
+    *out = h;
+    return GPBO_OK;
+}
+
+int gpbo_optpool_destroy(gpbo_optpool* h) {
+    delete h;
+    return GPBO_OK;
+}
+
+int gpbo_optpool_live(gpbo_optpool* h, int* idx, double* theta, int* n_live) {
+    if (!h || !idx || !theta || !n_live) return fail(GPBO_EINVAL, "optpool_live: bad argument");
+    int n = 0;
+    const int B = (int)h->pool.opt.size();
     for (int b = 0; b < B; ++b) {
-        for (int i = 0; i < 3; ++i) theta_opt[3 * (size_t)b + i] = opt[b].x[i];
-        fun[b] = opt[b].f;
-        if (nfev) nfev[b] = opt[b].nfev;
-        if (nit) nit[b] = opt[b].nit;
-        if (opt_status) opt_status[b] = opt[b].status;
+        const Lbfgsb& o = h->pool.opt[b];
+        if (!o.running()) continue;
+        idx[n] = b;
+        theta[3 * n] = o.x[0]; theta[3 * n + 1] = o.x[1]; theta[3 * n + 2] = o.x[2];
+        ++n;
     }
-    if (total_evals) *total_evals = evals;
-    if (rounds) *rounds = nround;
+    *n_live = n;
+    return GPBO_OK;
+}
+
+int gpbo_optpool_feed(gpbo_optpool* h, int n, const int* idx, const double* lml, const double* grad) {
+    if (!h || n < 0 || (n > 0 && (!idx || !lml || !grad))) return fail(GPBO_EINVAL, "optpool_feed: bad argument");
+    const int B = (int)h->pool.opt.size();
+    for (int k = 0; k < n; ++k) {
+        const int b = idx[k];
+        if (b < 0 || b >= B || !h->pool.opt[b].running()) return fail(GPBO_EINVAL, "optpool_feed: pair is not running");
+        double gneg[3] = {-grad[3 * k], -grad[3 * k + 1], -grad[3 * k + 2]};
+        h->pool.opt[b].feed(-lml[k], gneg);         // obj_func = (-lml, -grad), _gpr.py:300-307
+    }
+    h->pool.evals += n;
+    if (n > 0) h->pool.rounds += 1;
+    return GPBO_OK;
+}
+
+int gpbo_optpool_result(gpbo_optpool* h, double* theta_opt, double* fun, int* nfev, int* nit, int* opt_status,
+                        long long* total_evals, int* rounds) {
+    if (!h || !theta_opt || !fun) return fail(GPBO_EINVAL, "optpool_result: bad argument");
+    pool_result(h->pool, theta_opt, fun, nfev, nit, opt_status);
+    if (total_evals) *total_evals = h->pool.evals;
+    if (rounds) *rounds = h->pool.rounds;
+    return GPBO_OK;
+}
+
+int gpbo_problem_upload_host(gpbo_ctx* c, const double* t, const double* y, int G, int m) {
+    if (!c || !t || !y || G <= 0 || m <= 0) return fail(GPBO_EINVAL, "problem_upload_host: bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc = upload_problem(c, c->stream, t, y, G, m);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->G_res = G; c->m_res = m;
+    return GPBO_OK;
+}
+
+int gpbo_lml_grad_resident_host(gpbo_ctx* c, const double* theta, const int* gp_of, int B, double* lml, double* grad,
+                                int* status) {
+    if (!c || !theta || !gp_of || !lml || !grad || B < 0) return fail(GPBO_EINVAL, "lml_grad_resident_host: bad argument");
+    if (c->G_res <= 0) return fail(GPBO_EINVAL, "lml_grad_resident_host: no resident problem (gpbo_problem_upload_host)");
+    if (B == 0) return GPBO_OK;
+    for (int b = 0; b < B; ++b)
+        if (gp_of[b] < 0 || gp_of[b] >= c->G_res) return fail(GPBO_EINVAL, "lml_grad_resident_host: gp_of entry out of range");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    int rc = ensure_round_buffers(c, B);
+    if (rc) return rc;
+    std::memcpy(c->h_theta, theta, (size_t)B * 24);
+    std::memcpy(c->h_gpof, gp_of, (size_t)B * 4);
+    CUDA_TRY(cudaMemcpyAsync(c->theta_dev.p, c->h_theta, (size_t)B * 24, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(c->gpof_dev.p, c->h_gpof, (size_t)B * 4, cudaMemcpyHostToDevice, s));
+    rc = lml_grad_device(c, s, c->t_dev.as<double>(), c->y_dev.as<double>(), c->G_res, c->m_res,
+                         c->theta_dev.as<double>(), c->gpof_dev.as<int>(), B, c->lml_dev.as<double>(),
+                         c->grad_dev.as<double>(), c->st_dev.as<int>());
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(lml, c->lml_dev.p, (size_t)B * 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(grad, c->grad_dev.p, (size_t)B * 24, cudaMemcpyDeviceToHost, s));
+    if (status) CUDA_TRY(cudaMemcpyAsync(status, c->st_dev.p, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
     return GPBO_OK;
 }
 
@@ -734,12 +1108,18 @@ static int moments_device(gpbo_ctx* c, cudaStream_t s, int mode, const double* t
     const int m_pad = pad_to_tile(m), n_pad = pad_to_tile(n), xT = n_pad / TB;
     const bool need_x = (mode == 0) || (cov != nullptr);
     const size_t extra = (need_x ? (size_t)n_pad * m_pad * 8 : 0) + (size_t)n_pad * 8;
-    const size_t reserved = (size_t)G * m_pad * 8 + (1 << 20);
+    // the covariance output (when it is the library's own staging buffer) lives beside the waves
+    const bool own_cov = cov && cov == c->cov_dev.as<double>();
+    const size_t reserved = (size_t)G * m_pad * 8 + (1 << 20) + (own_cov ? c->cov_dev.bytes : 0);
     const int cap = wave_capacity(c, m_pad, extra, reserved, G);
     if (cap <= 0) return fail(GPBO_ENOMEM, "moments: one GP does not fit the workspace limit");
-    rc = ensure_wave(c, m_pad, cap);
-    if (rc) return rc;
-    if (need_x) CUDA_TRY(c->X.ensure((size_t)cap * n_pad * m_pad * 8));
+    {
+        std::vector<Need> more;
+        if (need_x) more.push_back({&c->X, (size_t)cap * n_pad * m_pad * 8});
+        if (own_cov) more.push_back({&c->cov_dev, c->cov_dev.bytes});
+        rc = ensure_wave(c, s, m_pad, cap, more);
+        if (rc) return rc;
+    }
     CUDA_TRY(c->trow.ensure((size_t)cap * n_pad * 8));
     CUDA_TRY(c->gpof_dev.ensure((size_t)G * 4));
     {
@@ -826,7 +1206,10 @@ static int moments_host(gpbo_ctx* c, int mode, const double* t, const double* y,
     CUDA_TRY(c->out1.ensure((size_t)G * n * 8));
     CUDA_TRY(c->out2.ensure((size_t)G * n * 8));
     CUDA_TRY(c->st_dev.ensure((size_t)G * 4));
-    if (cov) CUDA_TRY(c->cov_dev.ensure((size_t)G * n * n * 8));
+    if (cov) {
+        rc = fit_buffers(c, s, {{&c->cov_dev, (size_t)G * n * n * 8}});
+        if (rc) return rc;
+    }
     if (alpha) CUDA_TRY(c->grad_dev.ensure((size_t)G * m * 8));
     rc = moments_device(c, s, mode, c->t_dev.as<double>(), c->y_dev.as<double>(), G, m, c->theta_dev.as<double>(),
                         c->tsrc.as<double>(), pts_stride, n, c->out1.as<double>(), c->out2.as<double>(),
@@ -835,7 +1218,8 @@ static int moments_host(gpbo_ctx* c, int mode, const double* t, const double* y,
     if (rc) return rc;
     if (sqrtw) {
         if (!cov) return fail(GPBO_EINVAL, "lstsq_weights: cov output is required when sqrtw is requested");
-        CUDA_TRY(c->w_dev.ensure((size_t)G * n * n * 8));
+        rc = fit_buffers(c, s, {{&c->cov_dev, c->cov_dev.bytes}, {&c->w_dev, (size_t)G * n * n * 8}});
+        if (rc) return rc;
         rc = sqrtw_device(c, s, c->cov_dev.as<double>(), G, n, eta, c->w_dev.as<double>(), w_status, w_iters);
         if (rc) return rc;
         c->w_G = G; c->w_n = n;
@@ -881,8 +1265,8 @@ int gpbo_sqrtw_host(gpbo_ctx* c, const double* cov, int G, int n, double eta, do
     CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
     const size_t bytes = (size_t)G * n * n * 8;
-    CUDA_TRY(c->cov_dev.ensure(bytes));
-    CUDA_TRY(c->w_dev.ensure(bytes));
+    int rc0 = fit_buffers(c, s, {{&c->cov_dev, bytes}, {&c->w_dev, bytes}});
+    if (rc0) return rc0;
     CUDA_TRY(cudaMemcpyAsync(c->cov_dev.p, cov, bytes, cudaMemcpyHostToDevice, s));
     int rc = sqrtw_device(c, s, c->cov_dev.as<double>(), G, n, eta, c->w_dev.as<double>(), status, iters);
     if (rc) return rc;

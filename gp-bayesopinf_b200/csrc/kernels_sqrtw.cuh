@@ -5,8 +5,15 @@
 // Newton-Schulz iteration (Higham, Functions of Matrices, eq. 6.35), which is nothing but symmetric GEMMs and
 // therefore runs on the same FP64 DMMA tile engine as the Cholesky:
 //     A_s = (C + eta I) / s,  s = ||C + eta I||_inf  (so 0 < lambda(A_s) <= 1)
-//     Y_0 = A_s, Z_0 = I;   T_k = Z_k Y_k;   Y_{k+1} = 1.5 Y_k - 0.5 Y_k T_k;   Z_{k+1} = 1.5 Z_k - 0.5 T_k Z_k
+//     Y_0 = A_s, Z_0 = I;   T_k = Z_k Y_k;   Y_{k+1} = a_k Y_k - b_k Y_k T_k;   Z_{k+1} = a_k Z_k - b_k T_k Z_k
 //     Y_k -> A_s^(1/2), Z_k -> A_s^(-1/2), T_k -> I (quadratically once ||I - T|| < 1);  sqrtW = Z / sqrt(s).
+// Plain Newton-Schulz has a_k = 1.5, b_k = 0.5 and lifts a small eigenvalue of T by only 2.25 per step (31 steps
+// for cond 1e11).  The steps are therefore SCALED (Chen & Chow 2014, stable scaling of Newton-Schulz): with x^2 an
+// eigenvalue of T_k in [l_k^2, 1], the substitution (Y, Z) -> (mu Y, mu Z), mu_k = sqrt(3 / (1 + l_k + l_k^2)), gives
+// a_k = 1.5 mu_k, b_k = 0.5 mu_k^3 and x -> mu x (3 - mu^2 x^2) / 2, which still maps (0, 1] into (0, 1] for every
+// mu in [1, sqrt 3] (so a wrong bound l only costs speed) but lifts small eigenvalues of T by up to 6.75 per step:
+// 13 steps for cond 1e11.  l_0 = sqrt(eta / s) (lambda_min(C + eta I) >= eta for a covariance C), l_{k+1} = the
+// image of l_k; mu_k -> 1 as l_k -> 1, where the iteration is the plain quadratically convergent one.
 // All iterates are polynomials in A_s, hence symmetric and commuting in exact arithmetic, so every product can be
 // written as an "NT" product of row blocks.  Y and Z are kept exactly symmetric (tiles I >= J computed, mirrored);
 // T = Z Y must NOT be symmetrised -- replacing it by its mirrored lower triangle perturbs the coupling and the
@@ -76,9 +83,9 @@ __global__ void __launch_bounds__(NTHR) ns_init_kernel(const double* __restrict_
 
 // which = first_which + blockIdx.y:
 //   0: T  = Z Y (every tile; T^T written alongside),  part[p][tile] = sum (delta - T)^2 over the tile
-//   1: Yn = 1.5 Y - 0.5 Y T  (tiles I >= J, mirrored)      2: Zn = 1.5 Z - 0.5 T Z  (tiles I >= J, mirrored)
+//   1: Yn = ca Y - cb Y T  (tiles I >= J, mirrored)      2: Zn = ca Z - cb T Z  (tiles I >= J, mirrored)
 // ntiles = nT * nT for which 0, nT (nT + 1) / 2 otherwise.
-__global__ void __launch_bounds__(NTHR, 1) ns_gemm_kernel(NsArgs a, int ntiles, int first_which) {
+__global__ void __launch_bounds__(NTHR, 1) ns_gemm_kernel(NsArgs a, int ntiles, int first_which, double ca, double cb) {
     extern __shared__ __align__(16) double smem[];
     const ThreadCoord tc;
     const int p = blockIdx.x / ntiles, q = blockIdx.x % ntiles;
@@ -128,8 +135,8 @@ __global__ void __launch_bounds__(NTHR, 1) ns_gemm_kernel(NsArgs a, int ntiles, 
                 }
             } else {
                 const double2 x = *reinterpret_cast<const double2*>(X + (long)r * a.ld + c0);
-                v[0] = 1.5 * x.x - 0.5 * v[0];
-                v[1] = 1.5 * x.y - 0.5 * v[1];
+                v[0] = ca * x.x - cb * v[0];
+                v[1] = ca * x.y - cb * v[1];
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int c = c0 + e;

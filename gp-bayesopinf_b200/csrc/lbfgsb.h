@@ -16,12 +16,30 @@
 //
 // Reverse communication lets the caller evaluate f and g for ALL live optimisers in one batched
 // GPU launch per lock-step round (BASELINE.json north_star (3)).
+//
+// Every function is __host__ __device__: the lock-step driver of the large-matrix path runs the state machines on
+// the host (gpbo_fit_host, gpbo_optpool_*), the persistent kernel of the small-matrix path (kernels_small.cuh)
+// runs the very same code on thread 0 of each CTA.
 #pragma once
 #include <cmath>
 #include <cfloat>
-#include <algorithm>
+
+#ifdef __CUDACC__
+#define GPBO_HD __host__ __device__
+#else
+#define GPBO_HD
+#endif
 
 namespace gpbo {
+
+// exact, so host and device runs agree bit for bit
+GPBO_HD inline double lb_max(double a, double b) { return a > b ? a : b; }
+GPBO_HD inline double lb_min(double a, double b) { return a < b ? a : b; }
+GPBO_HD inline double lb_abs(double a) { return a < 0.0 ? -a : (a == 0.0 ? 0.0 : a); }
+GPBO_HD inline bool lb_finite(double a) { return (a - a) == 0.0; }
+GPBO_HD inline double lb_sqrt(double a) { return sqrt(a); }
+template <class T>
+GPBO_HD inline void lb_swap(T& a, T& b) { T c = a; a = b; b = c; }
 
 constexpr int LB_N = 3;
 constexpr int LB_M = 10;
@@ -51,11 +69,11 @@ struct LineSearch {
     double ginit, gtest, gx, gy, finit, fx, fy, stx, sty, stmin, stmax, width, width1;
     enum Task { FG, CONVERGED, WARNING, ERROR } task;
 
-    static void step(double& stx, double& fx, double& dx, double& sty, double& fy, double& dy, double& stp,
+    GPBO_HD static void step(double& stx, double& fx, double& dx, double& sty, double& fy, double& dy, double& stp,
                      double fp, double dp, bool& brackt, double stpmin, double stpmax) {
-        const double sgnd = dp * (dx / std::fabs(dx));
+        const double sgnd = dp * (dx / lb_abs(dx));
         double stpf, stpc, stpq, theta, s, gamma, p, q, r;
-        if (!std::isfinite(fp) || !std::isfinite(dp)) {
+        if (!lb_finite(fp) || !lb_finite(dp)) {
             // Objective undefined at the trial point (Cholesky failed): bisect back towards stx.
             brackt = true;
             sty = stp; fy = fp; dy = dp;
@@ -64,34 +82,34 @@ struct LineSearch {
         }
         if (fp > fx) {
             theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
-            s = std::max(std::fabs(theta), std::max(std::fabs(dx), std::fabs(dp)));
-            gamma = s * std::sqrt((theta / s) * (theta / s) - (dx / s) * (dp / s));
+            s = lb_max(lb_abs(theta), lb_max(lb_abs(dx), lb_abs(dp)));
+            gamma = s * lb_sqrt((theta / s) * (theta / s) - (dx / s) * (dp / s));
             if (stp < stx) gamma = -gamma;
             p = (gamma - dx) + theta;
             q = ((gamma - dx) + gamma) + dp;
             r = p / q;
             stpc = stx + r * (stp - stx);
             stpq = stx + ((dx / ((fx - fp) / (stp - stx) + dx)) / 2.0) * (stp - stx);
-            if (std::fabs(stpc - stx) < std::fabs(stpq - stx)) stpf = stpc;
+            if (lb_abs(stpc - stx) < lb_abs(stpq - stx)) stpf = stpc;
             else stpf = stpc + (stpq - stpc) / 2.0;
             brackt = true;
         } else if (sgnd < 0.0) {
             theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
-            s = std::max(std::fabs(theta), std::max(std::fabs(dx), std::fabs(dp)));
-            gamma = s * std::sqrt((theta / s) * (theta / s) - (dx / s) * (dp / s));
+            s = lb_max(lb_abs(theta), lb_max(lb_abs(dx), lb_abs(dp)));
+            gamma = s * lb_sqrt((theta / s) * (theta / s) - (dx / s) * (dp / s));
             if (stp > stx) gamma = -gamma;
             p = (gamma - dp) + theta;
             q = ((gamma - dp) + gamma) + dx;
             r = p / q;
             stpc = stp + r * (stx - stp);
             stpq = stp + (dp / (dp - dx)) * (stx - stp);
-            if (std::fabs(stpc - stp) > std::fabs(stpq - stp)) stpf = stpc;
+            if (lb_abs(stpc - stp) > lb_abs(stpq - stp)) stpf = stpc;
             else stpf = stpq;
             brackt = true;
-        } else if (std::fabs(dp) < std::fabs(dx)) {
+        } else if (lb_abs(dp) < lb_abs(dx)) {
             theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
-            s = std::max(std::fabs(theta), std::max(std::fabs(dx), std::fabs(dp)));
-            gamma = s * std::sqrt(std::max(0.0, (theta / s) * (theta / s) - (dx / s) * (dp / s)));
+            s = lb_max(lb_abs(theta), lb_max(lb_abs(dx), lb_abs(dp)));
+            gamma = s * lb_sqrt(lb_max(0.0, (theta / s) * (theta / s) - (dx / s) * (dp / s)));
             if (stp > stx) gamma = -gamma;
             p = (gamma - dp) + theta;
             q = (gamma + (dx - dp)) + gamma;
@@ -101,21 +119,21 @@ struct LineSearch {
             else stpc = stpmin;
             stpq = stp + (dp / (dp - dx)) * (stx - stp);
             if (brackt) {
-                if (std::fabs(stpc - stp) < std::fabs(stpq - stp)) stpf = stpc;
+                if (lb_abs(stpc - stp) < lb_abs(stpq - stp)) stpf = stpc;
                 else stpf = stpq;
-                if (stp > stx) stpf = std::min(stp + 0.66 * (sty - stp), stpf);
-                else stpf = std::max(stp + 0.66 * (sty - stp), stpf);
+                if (stp > stx) stpf = lb_min(stp + 0.66 * (sty - stp), stpf);
+                else stpf = lb_max(stp + 0.66 * (sty - stp), stpf);
             } else {
-                if (std::fabs(stpc - stp) > std::fabs(stpq - stp)) stpf = stpc;
+                if (lb_abs(stpc - stp) > lb_abs(stpq - stp)) stpf = stpc;
                 else stpf = stpq;
-                stpf = std::min(stpmax, stpf);
-                stpf = std::max(stpmin, stpf);
+                stpf = lb_min(stpmax, stpf);
+                stpf = lb_max(stpmin, stpf);
             }
         } else {
             if (brackt) {
                 theta = 3.0 * (fp - fy) / (sty - stp) + dy + dp;
-                s = std::max(std::fabs(theta), std::max(std::fabs(dy), std::fabs(dp)));
-                gamma = s * std::sqrt((theta / s) * (theta / s) - (dy / s) * (dp / s));
+                s = lb_max(lb_abs(theta), lb_max(lb_abs(dy), lb_abs(dp)));
+                gamma = s * lb_sqrt((theta / s) * (theta / s) - (dy / s) * (dp / s));
                 if (stp > sty) gamma = -gamma;
                 p = (gamma - dp) + theta;
                 q = ((gamma - dp) + gamma) + dy;
@@ -134,7 +152,7 @@ struct LineSearch {
         stp = stpf;
     }
 
-    void start(double f, double g, double& stp, double stpmax_) {
+    GPBO_HD void start(double f, double g, double& stp, double stpmax_) {
         (void)stpmax_;
         brackt = false;
         stage = 1;
@@ -150,7 +168,7 @@ struct LineSearch {
 
     static constexpr double ftol = 1e-3, gtol = 0.9, xtol = 0.1;
 
-    void iterate(double f, double g, double& stp, double stpmin, double stpmax) {
+    GPBO_HD void iterate(double f, double g, double& stp, double stpmin, double stpmax) {
         const double ftest = finit + stp * gtest;
         if (stage == 1 && f <= ftest && g >= 0.0) stage = 2;
         task = FG;
@@ -158,7 +176,7 @@ struct LineSearch {
         if (brackt && stmax - stmin <= xtol * stmax) task = WARNING;           // xtol test satisfied
         if (stp == stpmax && f <= ftest && g <= gtest) task = WARNING;         // stp = stpmax
         if (stp == stpmin && (f > ftest || g >= gtest)) task = WARNING;        // stp = stpmin
-        if (f <= ftest && std::fabs(g) <= gtol * (-ginit)) task = CONVERGED;
+        if (f <= ftest && lb_abs(g) <= gtol * (-ginit)) task = CONVERGED;
         if (task != FG) return;
         if (stage == 1 && f <= fx && f > ftest) {
             const double fm = f - stp * gtest;
@@ -172,19 +190,19 @@ struct LineSearch {
             step(stx, fx, gx, sty, fy, gy, stp, f, g, brackt, stmin, stmax);
         }
         if (brackt) {
-            if (std::fabs(sty - stx) >= 0.66 * width1) stp = stx + 0.5 * (sty - stx);
+            if (lb_abs(sty - stx) >= 0.66 * width1) stp = stx + 0.5 * (sty - stx);
             width1 = width;
-            width = std::fabs(sty - stx);
+            width = lb_abs(sty - stx);
         }
         if (brackt) {
-            stmin = std::min(stx, sty);
-            stmax = std::max(stx, sty);
+            stmin = lb_min(stx, sty);
+            stmax = lb_max(stx, sty);
         } else {
             stmin = stp + 1.1 * (stp - stx);
             stmax = stp + 4.0 * (stp - stx);
         }
-        stp = std::max(stp, stpmin);
-        stp = std::min(stp, stpmax);
+        stp = lb_max(stp, stpmin);
+        stp = lb_min(stp, stpmax);
         if ((brackt && (stp <= stmin || stp >= stmax)) || (brackt && stmax - stmin <= xtol * stmax)) stp = stx;
     }
 };
@@ -211,28 +229,37 @@ struct Lbfgsb {
 
     // Start at x0 (clipped into the box like scipy, _lbfgsb_py.py:359). The caller must then
     // evaluate f, g at `x` and call feed().
-    void init(const double* x0, const double* lo, const double* hi, const LbOptions& o) {
+    GPBO_HD void init(const double* x0, const double* lo, const double* hi, const LbOptions& o) {
         opt = o;
+        if (opt.maxls < 1) opt.maxls = 1;
         for (int i = 0; i < LB_N; ++i) {
             l[i] = lo[i]; u[i] = hi[i];
-            x[i] = std::min(std::max(x0[i], l[i]), u[i]);
+            x[i] = lb_min(lb_max(x0[i], l[i]), u[i]);
         }
         status = LB_RUNNING; nfev = 0; nit = 0; col = 0; head = 0; theta = 1.0; first_eval = true;
     }
-    bool running() const { return status == LB_RUNNING; }
+    GPBO_HD bool running() const { return status == LB_RUNNING; }
 
-    double projgr() const {
+    // Best point so far: the result once terminated; while running (a driver that stops after a fixed number of
+    // rounds) the last accepted iterate, i.e. the start of the current line search.
+    GPBO_HD void current_best(double* xb, double* fb) const {
+        const bool at_iterate = status == LB_RUNNING && !first_eval;
+        for (int i = 0; i < LB_N; ++i) xb[i] = at_iterate ? t[i] : x[i];
+        *fb = at_iterate ? fold : (first_eval ? HUGE_VAL : f);
+    }
+
+    GPBO_HD double projgr() const {
         double nrm = 0.0;
         for (int i = 0; i < LB_N; ++i) {
             double gi = g[i];
-            if (gi < 0.0) gi = std::max(x[i] - u[i], gi);
-            else gi = std::min(x[i] - l[i], gi);
-            nrm = std::max(nrm, std::fabs(gi));
+            if (gi < 0.0) gi = lb_max(x[i] - u[i], gi);
+            else gi = lb_min(x[i] - l[i], gi);
+            nrm = lb_max(nrm, lb_abs(gi));
         }
         return nrm;
     }
 
-    void dense_B(double B[LB_N][LB_N]) const {
+    GPBO_HD void dense_B(double B[LB_N][LB_N]) const {
         for (int i = 0; i < LB_N; ++i)
             for (int j = 0; j < LB_N; ++j) B[i][j] = (i == j) ? theta : 0.0;
         for (int k = 0; k < col; ++k) {
@@ -251,7 +278,7 @@ struct Lbfgsb {
     }
 
     // Generalized Cauchy point along the projected steepest-descent path. iwhere: 0 free, 1 at lower, 2 at upper.
-    void cauchy(const double B[LB_N][LB_N], double sbgnrm, double* xcp, int* iwhere) const {
+    GPBO_HD void cauchy(const double B[LB_N][LB_N], double sbgnrm, double* xcp, int* iwhere) const {
         for (int i = 0; i < LB_N; ++i) { xcp[i] = x[i]; iwhere[i] = 0; }
         if (sbgnrm <= 0.0) return;
         double dd[LB_N], tb[LB_N];
@@ -262,13 +289,14 @@ struct Lbfgsb {
             const bool xlower = tl <= 0.0, xupper = tu <= 0.0;
             if (xlower && neggi <= 0.0) iwhere[i] = 1;
             else if (xupper && neggi >= 0.0) iwhere[i] = 2;
-            else if (std::fabs(neggi) <= 0.0) iwhere[i] = -3;
+            else if (lb_abs(neggi) <= 0.0) iwhere[i] = -3;
             if (iwhere[i] != 0) { dd[i] = 0.0; tb[i] = HUGE_VAL; continue; }
             dd[i] = neggi;
             tb[i] = neggi < 0.0 ? tl / (-neggi) : tu / neggi;
             order[nbreak++] = i;
         }
-        std::sort(order, order + nbreak, [&](int a, int b) { return tb[a] < tb[b]; });
+        for (int a = 1; a < nbreak; ++a)                       // insertion sort of <= 3 breakpoints
+            for (int b = a; b > 0 && tb[order[b]] < tb[order[b - 1]]; --b) lb_swap(order[b], order[b - 1]);
         auto derivs = [&](const double* zz, double& f1, double& f2) {
             f1 = 0.0; f2 = 0.0;
             for (int i = 0; i < LB_N; ++i) {
@@ -297,11 +325,11 @@ struct Lbfgsb {
             zz[ibp] = xcp[ibp] - x[ibp];
             if (b == nbreak - 1) { all_fixed = true; dtm = 0.0; break; }
             derivs(zz, f1, f2);
-            f2 = std::max(DBL_EPSILON * f2_org, f2);
+            f2 = lb_max(DBL_EPSILON * f2_org, f2);
             dtm = -f1 / f2;
         }
         if (!all_fixed) {
-            dtm = std::max(dtm, 0.0);
+            dtm = lb_max(dtm, 0.0);
             tsum += dtm;
         }
         for (int i = 0; i < LB_N; ++i)
@@ -309,7 +337,7 @@ struct Lbfgsb {
     }
 
     // Subspace minimisation over the free variables, followed by projection (or backtracking).
-    void subsm(const double B[LB_N][LB_N], const int* iwhere, double* xcp) const {
+    GPBO_HD void subsm(const double B[LB_N][LB_N], const int* iwhere, double* xcp) const {
         int fr[LB_N], nf = 0;
         for (int i = 0; i < LB_N; ++i)
             if (iwhere[i] <= 0) fr[nf++] = i;
@@ -327,10 +355,10 @@ struct Lbfgsb {
         for (int k = 0; k < nf; ++k) {
             int piv = k;
             for (int a = k + 1; a < nf; ++a)
-                if (std::fabs(M[a][k]) > std::fabs(M[piv][k])) piv = a;
+                if (lb_abs(M[a][k]) > lb_abs(M[piv][k])) piv = a;
             if (M[piv][k] == 0.0) return;
             if (piv != k)
-                for (int b = 0; b <= nf; ++b) std::swap(M[k][b], M[piv][b]);
+                for (int b = 0; b <= nf; ++b) lb_swap(M[k][b], M[piv][b]);
             for (int a = k + 1; a < nf; ++a) {
                 const double fct = M[a][k] / M[k][k];
                 for (int b = k; b <= nf; ++b) M[a][b] -= fct * M[k][b];
@@ -343,7 +371,7 @@ struct Lbfgsb {
             dsub[a] = s / M[a][a];
         }
         for (int a = 0; a < nf; ++a)
-            if (!std::isfinite(dsub[a])) return;
+            if (!lb_finite(dsub[a])) return;
         // projected point
         double xp[LB_N];
         for (int i = 0; i < LB_N; ++i) xp[i] = xcp[i];
@@ -353,7 +381,7 @@ struct Lbfgsb {
         for (int a = 0; a < nf; ++a) {
             const int k = fr[a];
             const double v = xcp[k] + dsub[a];
-            xn[k] = std::max(l[k], std::min(u[k], v));
+            xn[k] = lb_max(l[k], lb_min(u[k], v));
             if (xn[k] != v) projected = true;
         }
         double ddp = 0.0;
@@ -388,25 +416,25 @@ struct Lbfgsb {
         for (int i = 0; i < LB_N; ++i) xcp[i] = xn[i];
     }
 
-    void reset_memory() { col = 0; head = 0; theta = 1.0; }
+    GPBO_HD void reset_memory() { col = 0; head = 0; theta = 1.0; }
 
     // Build the search direction for the current iterate and start the line search.
     // Returns false when the optimiser terminated instead.
-    bool new_iteration() {
+    GPBO_HD bool new_iteration() {
         for (int attempt = 0; attempt < 2; ++attempt) {
             double B[LB_N][LB_N];
             dense_B(B);
             bool okB = true;
             for (int i = 0; i < LB_N; ++i)
                 for (int j = 0; j < LB_N; ++j)
-                    if (!std::isfinite(B[i][j])) okB = false;
+                    if (!lb_finite(B[i][j])) okB = false;
             if (!okB) { reset_memory(); dense_B(B); }
             int iwhere[LB_N];
             cauchy(B, projgr(), z, iwhere);
             if (col > 0) subsm(B, iwhere, z);
             double dtd = 0.0;
             for (int i = 0; i < LB_N; ++i) { d[i] = z[i] - x[i]; dtd += d[i] * d[i]; }
-            dnorm = std::sqrt(dtd);
+            dnorm = lb_sqrt(dtd);
             stpmx = 1e10;
             if (nit == 0) stpmx = 1.0;
             else
@@ -436,14 +464,19 @@ struct Lbfgsb {
                 continue;
             }
             ls.start(f, gd, stp, stpmx);
-            return advance_trial();
+            // first trial point of the line search: advance_trial() with ifun = 0, written out so that the call
+            // graph stays acyclic (the device build then needs no recursion stack); maxls >= 1 is enforced in init()
+            ifun = 1; iback = 0;
+            if (stp == 1.0) for (int i = 0; i < LB_N; ++i) x[i] = z[i];
+            else for (int i = 0; i < LB_N; ++i) x[i] = stp * d[i] + t[i];
+            return true;
         }
         status = LB_ABNORMAL;
         return false;
     }
 
     // Move x to the next trial point of the line search; false if the evaluation budget is spent.
-    bool advance_trial() {
+    GPBO_HD bool advance_trial() {
         ifun += 1;
         iback = ifun - 1;
         if (iback >= opt.maxls) return line_search_failed();
@@ -452,7 +485,7 @@ struct Lbfgsb {
         return true;
     }
 
-    bool line_search_failed() {
+    GPBO_HD bool line_search_failed() {
         for (int i = 0; i < LB_N; ++i) { x[i] = t[i]; g[i] = r[i]; }
         f = fold;
         if (col == 0) { status = LB_ABNORMAL; return false; }
@@ -462,13 +495,13 @@ struct Lbfgsb {
 
     // Provide f(x), g(x) for the current x. Afterwards either running() is false or x holds the next
     // point to evaluate.
-    void feed(double fv, const double* gv) {
+    GPBO_HD void feed(double fv, const double* gv) {
         nfev += 1;
         if (first_eval) {
             first_eval = false;
             f = fv;
             for (int i = 0; i < LB_N; ++i) g[i] = gv[i];
-            if (!std::isfinite(fv)) { status = LB_BAD_START; return; }
+            if (!lb_finite(fv)) { status = LB_BAD_START; return; }
             if (projgr() <= opt.pgtol) { status = LB_CONV_PGTOL; return; }
             new_iteration();
             return;
@@ -482,12 +515,12 @@ struct Lbfgsb {
             advance_trial();
             return;
         }
-        if (!std::isfinite(fv)) { line_search_failed(); return; }
+        if (!lb_finite(fv)) { line_search_failed(); return; }
         // line search finished: x is the new iterate
         nit += 1;
         const double sbgnrm = projgr();
         if (sbgnrm <= opt.pgtol) { status = LB_CONV_PGTOL; return; }
-        const double ddum = std::max(std::max(std::fabs(fold), std::fabs(f)), 1.0);
+        const double ddum = lb_max(lb_max(lb_abs(fold), lb_abs(f)), 1.0);
         if (fold - f <= DBL_EPSILON * opt.factr * ddum) { status = LB_CONV_FACTR; return; }
         if (nit >= opt.maxiter) { status = LB_MAXITER; return; }
         if (nfev > opt.maxfun) { status = LB_MAXFUN; return; }

@@ -25,8 +25,22 @@ from . import _lib
 __all__ = ["GP_RBFW", "GP_MaternW", "ConvergenceWarning"]
 
 
-class ConvergenceWarning(UserWarning):
-    """Optimum close to a bound / optimiser did not converge (sklearn emits the same class name)."""
+def _convergence_warning_class():
+    """The warning CLASS scikit-learn raises (``_gpr.py:338, 667``) when scikit-learn is installed -- users of the
+    reference filter on ``sklearn.exceptions.ConvergenceWarning`` -- else a local class of the same name.  Only the
+    exception module is touched: no scikit-learn / SciPy numerics are ever used by this package."""
+    import importlib
+
+    try:
+        return importlib.import_module("sklearn.exceptions").ConvergenceWarning
+    except Exception:
+        class ConvergenceWarning(UserWarning):
+            """Optimum close to a bound / optimiser did not converge."""
+
+        return ConvergenceWarning
+
+
+ConvergenceWarning = _convergence_warning_class()
 
 
 # ---- tiny stand-ins for the sklearn objects whose attributes the reference reads --------------
@@ -99,18 +113,33 @@ class _GPRState:
 
 
 def _check_bounds(theta, bounds_log, names=("k1__k1__constant_value", "k1__k2__length_scale", "k2__noise_level")):
-    """sklearn kernels.py:436-465: warn when the optimum sits on a bound."""
+    """sklearn ``kernels.py:436-465`` (``_check_bounds_params``): warn when the optimum sits on a bound.  Like
+    sklearn, the comparison is ``np.isclose`` on the LOG values (theta against the log-bounds)."""
+    theta = np.asarray(theta, dtype=np.float64)
     for i, name in enumerate(names):
-        lo, hi = np.exp(bounds_log[i])
-        v = np.exp(theta[i])
-        if np.isclose(theta[i], bounds_log[i, 0], atol=1e-12, rtol=0) or np.isclose(v, lo):
+        if np.isclose(theta[i], bounds_log[i, 0]):
             warnings.warn(f"The optimal value found for dimension 0 of parameter {name} is close to the specified "
-                          f"lower bound {lo}. Decreasing the bound and calling fit again may find a better value.",
-                          ConvergenceWarning)
-        elif np.isclose(v, hi):
+                          f"lower bound {np.exp(bounds_log[i, 0])}. Decreasing the bound and calling fit again may "
+                          "find a better value.", ConvergenceWarning)
+        if np.isclose(theta[i], bounds_log[i, 1]):
             warnings.warn(f"The optimal value found for dimension 0 of parameter {name} is close to the specified "
-                          f"upper bound {hi}. Increasing the bound and calling fit again may find a better value.",
-                          ConvergenceWarning)
+                          f"upper bound {np.exp(bounds_log[i, 1])}. Increasing the bound and calling fit again may "
+                          "find a better value.", ConvergenceWarning)
+
+
+_LBFGS_STATUS = {2: "ABNORMAL_TERMINATION_IN_LNSRCH", 3: "STOP: TOTAL NO. of ITERATIONS REACHED LIMIT",
+                 4: "STOP: TOTAL NO. of f AND g EVALUATIONS EXCEEDS LIMIT"}
+
+
+def _warn_unconverged_starts(statuses):
+    """sklearn checks EVERY start's optimiser result (``_gpr.py:667`` -> ``_check_optimize_result``) and warns for
+    each one that did not converge, not only for the best."""
+    for st in np.asarray(statuses).ravel():
+        msg = _LBFGS_STATUS.get(int(st))
+        if msg is not None:
+            warnings.warn(f"lbfgs failed to converge (status={int(st)}):\n{msg}.\n\nIncrease the number of iterations "
+                          "(max_iter) or scale the data as shown in:\n"
+                          "    https://scikit-learn.org/stable/modules/preprocessing.html", ConvergenceWarning)
 
 
 def draw_restart_points(bounds_log, n_restarts):
@@ -196,8 +225,7 @@ class GP_RBFW:
         self.gpr.log_marginal_likelihood_value_ = -float(funs[best])
         self.gpr.X_train_ = np.array(t_training, dtype=np.float64)[:, None]
         self.gpr.y_train_ = np.array(training_data, dtype=np.float64)
-        if np.any(statuses[best:best + 1] == 2):
-            warnings.warn("lbfgs failed to converge (abnormal termination in line search).", ConvergenceWarning)
+        _warn_unconverged_starts(statuses)               # _gpr.py:667, once per start
 
     def _finish_fit(self, ctx, alpha=None, status=None):
         """alpha_ = K^-1 y at the selected theta (_gpr.py:349-367); non-PD -> LinAlgError."""
@@ -280,14 +308,18 @@ class GP_RBFW:
         self._set_lstsq_result(t_est, state[0], ddt[0], cov[0], int(st[0]), w[0], int(wst[0]))
         return None
 
-    def _set_lstsq_result(self, t_est, state, ddt, cov, status, sqrtW, w_status):
+    def _set_lstsq_result(self, t_est, state, ddt, cov, status, sqrtW, w_status, with_sqrtW=True):
+        """``cov`` / ``sqrtW`` may be None on a rank that does not hold them (multi-GPU, ``gather_cov=False``): the
+        attributes are then None; the status checks are the same on every rank."""
         self.t_estimation = t_est
-        if status != 0 or not np.all(np.isfinite(cov)):
+        if status != 0 or (cov is not None and not np.all(np.isfinite(cov))):
             # scipy.linalg.cho_factor(K_yy, check_finite=True) raises for the same inputs (gpkernels.py:481)
             raise np.linalg.LinAlgError("K_yy is not positive definite")
         self.state_estimate = state
         self.ddt_estimate = ddt
         self.ddt_covariance = cov
+        if not with_sqrtW:
+            return
         if w_status != 0:                                  # gpkernels.py:500-503
             raise ValueError("inverse covariance not positive definite, increase eta")
         self.sqrtW = sqrtW

@@ -56,17 +56,20 @@ def _as_time_matrix(time_domain_sampled, num_vars, sample_size):
 
 def fit_gaussian_processes(time_domain_training, time_domain_sampled, snapshots_sampled, gp_regularizer=1e-8, *,
                            constant_bounds=None, length_scale_bounds=None, noise_level_bounds=None,
-                           n_restarts_optimizer=None, verbose=True, group=None, want_sqrtW=True, kernel="rbf"):
+                           n_restarts_optimizer=None, verbose=True, group=None, want_sqrtW=True, kernel="rbf",
+                           gather_cov=True):
     """Fit one GP per row of ``snapshots_sampled`` and compute its least-squares data.
 
     Parameters follow the reference; ``time_domain_sampled`` may be one (m,) vector (PDE flavour) or a
     list of per-variable (m,) vectors (ODE flavour).  Returns ``list[GP_RBFW]``.
+
+    Multi-GPU (``group=True`` or a ``torch.distributed`` group): see ``fit_gaussian_processes_multi``.
     """
     gps = fit_gaussian_processes_multi(
         time_domain_training, [time_domain_sampled], [snapshots_sampled], gp_regularizer,
         constant_bounds=constant_bounds, length_scale_bounds=length_scale_bounds,
         noise_level_bounds=noise_level_bounds, n_restarts_optimizer=n_restarts_optimizer, verbose=verbose,
-        group=group, want_sqrtW=want_sqrtW, kernel=kernel)
+        group=group, want_sqrtW=want_sqrtW, kernel=kernel, gather_cov=gather_cov)
     return gps[0]
 
 
@@ -75,11 +78,20 @@ _KERNELS = {"rbf": 0, "matern32": 3, "matern52": 5}
 
 def fit_gaussian_processes_multi(time_domain_training, time_domains_sampled, snapshots_list, gp_regularizer=1e-8, *,
                                  constant_bounds=None, length_scale_bounds=None, noise_level_bounds=None,
-                                 n_restarts_optimizer=None, verbose=True, group=None, want_sqrtW=True, kernel="rbf"):
+                                 n_restarts_optimizer=None, verbose=True, group=None, want_sqrtW=True, kernel="rbf",
+                                 gather_cov=True):
     """Multi-trajectory form: the loop of ``PDEsMulti/main.py:99-109`` as ONE batch (L trajectories x r modes).
 
     ``time_domains_sampled[l]`` / ``snapshots_list[l]`` are trajectory l's sample times and (r, m) data.
     Returns ``gps[l][i]``.  All trajectories must share the sample count m (they do in the reference).
+
+    With a process group the evaluations of the optimiser are spread over the ranks (``sharding.fit_pairs``) and every
+    rank returns the same fitted GPs.  ``gather_cov=True`` (default) also gives every rank every GP's
+    ``ddt_covariance`` / ``sqrtW``, which the reference's step 3 reads for all modes (``PDEs/step3_estimate.py:212``,
+    ``PDEs/main.py:219``) -- so the rest of ``main.py`` runs unchanged on every rank.  ``gather_cov=False`` keeps the
+    two m' x m' matrices on the rank that computed them (GP g on rank ``g % world``) and sets them to ``None``
+    elsewhere: step 3 must then run where the matrices are.  Numerical failures (non-PD ``K_yy``, indefinite
+    ``C + eta I``) are all-gathered, so every rank raises the same exception.
     """
     if kernel not in _KERNELS:
         raise ValueError(f"kernel must be one of {sorted(_KERNELS)}")    # "rbf" is the reference's kernel
@@ -131,22 +143,17 @@ def fit_gaussian_processes_multi(time_domain_training, time_domains_sampled, sna
     theta_opt = np.array([o.gpr.kernel_.theta for o in objs])
 
     # 4. posterior moments of every GP in one batched pass
-    mom = sharding.moments(ctx, T, Y, theta_opt, t_est, group=group, eta=gp_regularizer if want_sqrtW else None)
+    mom = sharding.moments(ctx, T, Y, theta_opt, t_est, group=group, eta=gp_regularizer if want_sqrtW else None,
+                           gather_cov=gather_cov)
     for g in range(G):
         o = objs[g]
         o._finish_fit(ctx, alpha=mom["alpha"][g], status=int(mom["fit_status"][g]))
         if verbose:
             print(o)
-        cov = mom["cov"][g]
-        if cov is None:          # covariance lives on another rank
-            o.t_estimation = t_est
-            o.state_estimate, o.ddt_estimate = mom["state"][g], mom["ddt"][g]
-            continue
-        if want_sqrtW:
-            o._set_lstsq_result(t_est, mom["state"][g], mom["ddt"][g], cov, int(mom["status"][g]), mom["sqrtW"][g],
-                                int(mom["w_status"][g]))
-        else:
-            _set_no_sqrtW(o, t_est, mom, g)
+        # same checks, same exceptions on every rank (the statuses were all-gathered), matrices where they exist
+        o._set_lstsq_result(t_est, mom["state"][g], mom["ddt"][g], mom["cov"][g], int(mom["status"][g]),
+                            mom["sqrtW"][g] if want_sqrtW else None, int(mom["w_status"][g]) if want_sqrtW else 0,
+                            with_sqrtW=want_sqrtW)
 
     out, k = [], 0
     for Q in Ys:
@@ -154,7 +161,3 @@ def fit_gaussian_processes_multi(time_domain_training, time_domains_sampled, sna
         k += Q.shape[0]
     return out
 
-
-def _set_no_sqrtW(o, t_est, mom, g):
-    o.t_estimation = t_est
-    o.state_estimate, o.ddt_estimate, o.ddt_covariance = mom["state"][g], mom["ddt"][g], mom["cov"][g]

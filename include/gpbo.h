@@ -54,6 +54,17 @@ int gpbo_destroy(gpbo_ctx* ctx);
  * gpbo_lstsq_moments* are then the analytic d/dt' and d^2/dt'dt of the Matern kernel. */
 int gpbo_set_kernel_family(gpbo_ctx* ctx, int twice_nu);
 
+/* Training sizes m <= max_m (at most 224, the default) take the in-shared small-matrix path: one CTA per pair
+ * evaluates LML + gradient in ONE launch and gpbo_fit_host runs the whole multi-start fit as ONE persistent kernel
+ * with the L-BFGS-B state machines on the device (csrc/kernels_small.cuh) -- the regime of the reference's own
+ * experiments (m = 10 ... 200, ODEs/experiments.sh:11-18, PDEs/experiments.sh:13-26).  0 forces the blocked
+ * 128-tile path for every size. */
+int gpbo_set_small_path(gpbo_ctx* ctx, int max_m);
+
+/* The cudaStream_t on which the *_host entry points of this handle enqueue their copies and kernels (so that a
+ * caller can record CUDA events on it). */
+int gpbo_get_stream(gpbo_ctx* ctx, void** stream);
+
 /* Number of CUDA kernels this handle has launched so far (for bench accounting). */
 long long gpbo_launch_count(const gpbo_ctx* ctx);
 /* Number of pairs a wave can hold at training size m (derived from the memory limit). */
@@ -96,6 +107,30 @@ int gpbo_lml_grad_host(gpbo_ctx* ctx, const double* t, const double* y, int G, i
 int gpbo_fit_host(gpbo_ctx* ctx, const double* t, const double* y, int G, int m, const double* bounds_log,
                   const double* starts, const int* gp_of, int B, const double* opts, double* theta_opt,
                   double* fun, int* nfev, int* nit, int* opt_status, long long* total_evals, int* rounds);
+
+/* The pieces of gpbo_fit_host, for drivers that interleave a collective with every lock-step round (multi-GPU:
+ * gp-bayesopinf_b200/sharding.py re-balances the live pairs over the ranks each round and all-gathers the
+ * evaluations).  An optimiser pool holds the B L-BFGS-B state machines (host memory only, no CUDA device needed):
+ *   gpbo_optpool_live   -> the running pairs' indices idx[n] and current trial points theta[n][3] (arrays of B entries);
+ *   gpbo_optpool_feed   <- lml[n], grad[n][3] for pairs idx[n] (the pool minimises -lml like sklearn _gpr.py:300-307);
+ *   gpbo_optpool_result -> per-pair optimum as in gpbo_fit_host, total evaluations fed and number of feed rounds;
+ *                          a pair that is still running (driver stopped early) reports its last accepted iterate
+ *                          with opt_status -1.
+ * Replaces, together with gpbo_lml_grad_resident_host, the same reference loop as gpbo_fit_host. */
+typedef struct gpbo_optpool gpbo_optpool;
+int gpbo_optpool_create(gpbo_optpool** out, int B, const double* bounds_log, const double* starts, const double* opts);
+int gpbo_optpool_destroy(gpbo_optpool* pool);
+int gpbo_optpool_live(gpbo_optpool* pool, int* idx, double* theta, int* n_live);
+int gpbo_optpool_feed(gpbo_optpool* pool, int n, const int* idx, const double* lml, const double* grad);
+int gpbo_optpool_result(gpbo_optpool* pool, double* theta_opt, double* fun, int* nfev, int* nit, int* opt_status,
+                        long long* total_evals, int* rounds);
+
+/* Keep one problem (t, y: [G][m], HOST pointers) resident in HBM, then evaluate LML + gradient for batches of
+ * pairs against it (theta [B][3], gp_of [B], outputs as gpbo_lml_grad_host; all HOST pointers).  Any other *_host
+ * entry point of the handle replaces the resident problem. */
+int gpbo_problem_upload_host(gpbo_ctx* ctx, const double* t, const double* y, int G, int m);
+int gpbo_lml_grad_resident_host(gpbo_ctx* ctx, const double* theta, const int* gp_of, int B, double* lml,
+                                double* grad, int* status);
 
 /* Host-only driver of the SAME optimiser state machine that gpbo_fit_host advances in lock-step, for one
  * 3-parameter objective given as a callback (fn returns f and writes g[3]).  Needs no CUDA device.
@@ -156,9 +191,9 @@ int gpbo_weighted_products_host(gpbo_ctx* ctx, const double* sqrtw, int G, int n
 
 /* Per-kernel-class device timing (CUDA events on the launching stream), for bench.py's roofline.
  * Classes: 0 prep 1 chol_diag 2 chol_panel 3 trsv 4 trtri 5 lauum_grad 6 finalize 7 cross_panel
- *          8 schur 9 mean_std 10 assemble 11 sqrtw.  `ms` and `launches` are arrays of GPBO_NCLASS entries,
- * accumulated since the last gpbo_profile_enable(ctx, 1). */
-#define GPBO_NCLASS 12
+ *          8 schur 9 mean_std 10 assemble 11 sqrtw 12 small (in-shared path).  `ms` and `launches` are arrays of
+ * GPBO_NCLASS entries, accumulated since the last gpbo_profile_enable(ctx, 1). */
+#define GPBO_NCLASS 13
 int gpbo_profile_enable(gpbo_ctx* ctx, int on);
 int gpbo_profile_get(gpbo_ctx* ctx, double* ms, long long* launches);
 

@@ -90,6 +90,65 @@ def np_lml_grad(t, y, theta):
     return lml, grad, 0
 
 
+def np_lml_grad_lean(t, y, theta, block=1024, want_alpha=False):
+    """Same quantity as ``np_lml_grad`` (sklearn ``_gpr.py:583-651``, ``kernels.py:1559-1578``) for sizes where the
+    reference's m x m x 3 gradient tensor does not fit: K, L and K^-1 = cho_solve(L, I) are formed exactly as the
+    reference does (LAPACK dpotrf / dpotrs), the three traces 1/2 sum_ij (a_i a_j - K^-1_ij) dK_ij/dtheta_k are
+    accumulated over row blocks with dK regenerated on the fly.  Returns (lml, grad[3], status[, alpha])."""
+    y = np.asarray(y, dtype=np.float64)
+    sig2, ell, chi = np.exp(np.asarray(theta, dtype=np.float64))
+    x = np.asarray(t, dtype=np.float64) / ell
+    m = x.size
+    K = np.empty((m, m))
+    for i0 in range(0, m, block):
+        d = (x[i0:i0 + block, None] - x[None, :]) ** 2
+        K[i0:i0 + block] = sig2 * np.exp(-0.5 * d)
+    K[np.diag_indices(m)] = sig2 + chi              # R's diagonal is forced to 1 (kernels.py:1565)
+    try:
+        L = la.cholesky(K, lower=True, overwrite_a=True, check_finite=False)
+    except la.LinAlgError:
+        return (-np.inf, np.zeros(3), 1) + ((None,) if want_alpha else ())
+    alpha = la.cho_solve((L, True), y, check_finite=False)
+    lml = -0.5 * float(y @ alpha) - float(np.log(np.diag(L)).sum()) - 0.5 * m * LOG_2PI
+    Kinv = la.cho_solve((L, True), np.eye(m), overwrite_b=True, check_finite=False)
+    s = np.zeros(3)
+    for i0 in range(0, m, block):
+        i1 = min(m, i0 + block)
+        d = (x[i0:i1, None] - x[None, :]) ** 2
+        kr = sig2 * np.exp(-0.5 * d)
+        kr[np.arange(i1 - i0), np.arange(i0, i1)] = sig2
+        inner = np.outer(alpha[i0:i1], alpha) - Kinv[i0:i1]
+        s[0] += float(np.sum(inner * kr))
+        s[1] += float(np.sum(inner * (kr * d)))
+    s[2] = chi * float(np.sum(alpha * alpha - np.diag(Kinv)))
+    out = (lml, 0.5 * s, 0)
+    return out + ((alpha,) if want_alpha else ())
+
+
+def ld_truth(t, y, theta, exe=None):
+    """Extended-precision (80-bit) LML / gradient / alpha from ``oracle/lml_ld.c`` (built by ``oracle/Makefile`` into
+    ``oracle/_build/lml_ld``).  Returns (lml, grad[3], alpha[m])."""
+    import os
+    import struct
+    import subprocess
+    import tempfile
+
+    exe = exe or os.path.join(os.path.dirname(os.path.abspath(__file__)), "_build", "lml_ld")
+    t = np.ascontiguousarray(t, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    m = t.size
+    with tempfile.TemporaryDirectory() as d:
+        fin, fout = os.path.join(d, "in.bin"), os.path.join(d, "out.bin")
+        with open(fin, "wb") as f:
+            f.write(struct.pack("q", m))
+            f.write(t.tobytes())
+            f.write(y.tobytes())
+            f.write(np.ascontiguousarray(theta, dtype=np.float64).tobytes())
+        subprocess.run([exe, fin, fout], check=True)
+        o = np.fromfile(fout)
+    return float(o[0]), o[1:4].copy(), o[4:4 + m].copy()
+
+
 def np_alpha(t, y, theta):
     """alpha_ = K^-1 y at fixed theta (sklearn ``_gpr.py:349-367``)."""
     K = np_kernel(t, theta)

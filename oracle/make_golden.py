@@ -243,8 +243,117 @@ def make_fixed_theta(name="fixed_theta_synth", sizes=(64, 200, 333, 512, 1024)):
                         versions=np.array([f"{k}={x}" for k, x in v.items()]), **save)
 
 
+def _extreme_cond(K):
+    """cond_2 of a symmetric positive definite K from its extreme eigenvalues."""
+    import scipy.linalg as sla
+
+    m = K.shape[0]
+    lo = sla.eigvalsh(K, subset_by_index=[0, 0], check_finite=False)[0]
+    hi = sla.eigvalsh(K, subset_by_index=[m - 1, m - 1], check_finite=False)[0]
+    return float(hi / lo) if lo > 0 else float("inf")
+
+
+LARGE_THETAS = np.log(np.array([
+    [1.0, 0.1, 1e-3],
+    [2.5, 0.05, 1e-2],
+    [0.7, 0.3, 3e-3],
+]))
+
+
+def make_fixed_theta_large(name="fixed_theta_large", ref_sizes=(4096, 8192), lean_sizes=(16384,), truth=True,
+                           moments_m=4096, moments_n=512):
+    """The benchmarked sizes (BASELINE configs[3], [4] and the north star's n = 8192), GP 0 of the synthetic workload.
+
+    * m in ref_sizes: LML + gradient from the UNMODIFIED reference (GP_RBFW.gpr.log_marginal_likelihood);
+    * m in lean_sizes: the reference's m x m x 3 gradient tensor (6.4 GB at 16384, ~5 copies live) does not fit a
+      test-generation budget, so ``gp_oracle.np_lml_grad_lean`` (same LAPACK calls, traces by row blocks) is used;
+      it is checked against the unmodified reference at m = 4096 here and the agreement is stored;
+    * every (m, theta): the 80-bit long-double value of ``oracle/lml_ld.c`` ("truth") and the reference's own error
+      against it, so that a GPU test can ask "is the CUDA result as close to the truth as LAPACK's?";
+    * posterior moments (predict, compute_lstsq_matrices) of the unmodified reference at m = moments_m.
+    Only theta, LML, grad, alpha, cond and the inputs are stored."""
+    gpk = ref_import.load_reference_gpkernels()
+    import gp_oracle as orc
+
+    bounds = np.array([(1e-5, 1e5), (1e-5, 1e2), (1e-16, 1e2)])
+    thetas = LARGE_THETAS
+    save = dict(thetas=thetas, sizes=np.array(list(ref_sizes) + list(lean_sizes)),
+                ref_sizes=np.array(ref_sizes), lean_sizes=np.array(lean_sizes))
+
+    def new_gp(t, y, th):
+        gp = gpk.GP_RBFW(tuple(bounds[0]), tuple(bounds[1]), tuple(bounds[2]), 0)
+        gp.gpr.optimizer = None          # fixed-theta use only
+        gp.gpr.kernel.theta = th          # fit() then factors K(th): alpha_, L_ at th
+        gp.fit(t, y)
+        return gp
+
+    for m in list(ref_sizes) + list(lean_sizes):
+        t, y = orc.synthetic_trajectories(2, m, seed=m)
+        y0 = y[0]
+        nth = len(thetas) if m in ref_sizes else 2
+        lml, grad, cond = np.zeros(nth), np.zeros((nth, 3)), np.zeros(nth)
+        alpha = np.zeros((nth, m))
+        lean_gap = np.zeros((nth, 2))
+        for k in range(nth):
+            th = thetas[k]
+            t0 = time.time()
+            if m in ref_sizes:
+                gp = new_gp(t, y0, th)
+                l, gr = gp.gpr.log_marginal_likelihood(th, eval_gradient=True)
+                alpha[k] = gp.gpr.alpha_
+                K = gp.gpr.kernel_(t[:, None])
+                cond[k] = _extreme_cond(K)
+                del K
+                if m == min(ref_sizes):
+                    l2, g2, _ = orc.np_lml_grad_lean(t, y0, th)
+                    lean_gap[k] = abs(l2 - l) / abs(l), np.abs(g2 - gr).max() / np.abs(gr).max()
+                del gp
+            else:
+                l, gr, st, al = orc.np_lml_grad_lean(t, y0, th, want_alpha=True)
+                assert st == 0
+                alpha[k] = al
+                cond[k] = _extreme_cond(orc.np_kernel(t, th))
+            lml[k], grad[k] = l, gr
+            print(f"[large] m={m} k={k} lml={l!r} grad={gr} cond={cond[k]:.3e} ({time.time()-t0:.1f}s)", flush=True)
+        save[f"t_{m}"], save[f"y_{m}"] = t, y0
+        save[f"lml_{m}"], save[f"grad_{m}"], save[f"cond_{m}"], save[f"alpha_{m}"] = lml, grad, cond, alpha
+        if m == min(ref_sizes):
+            save["lean_vs_reference_rel"] = lean_gap
+
+    # posterior moments of the unmodified reference at the benchmarked size
+    m = moments_m
+    t, y = orc.synthetic_trajectories(2, m, seed=m)
+    th = thetas[0]
+    gp = new_gp(t, y[0], th)
+    t_est = np.linspace(0.0, 1.0, moments_n)
+    mean, std = gp.predict(t_est)
+    gp.compute_lstsq_matrices(t_est, eta=1e-8)
+    save.update(mom_m=m, mom_theta=th, mom_t_est=t_est, mom_pred_mean=mean, mom_pred_std=std,
+                mom_state=gp.state_estimate, mom_ddt=gp.ddt_estimate, mom_cov_diag=np.diag(gp.ddt_covariance).copy(),
+                mom_cov_sub=gp.ddt_covariance[::8, ::8].copy())
+    print("[large] moments done", flush=True)
+    v = versions()
+    path = os.path.join(GOLDEN_DIR, f"{name}.npz")
+    np.savez_compressed(path, versions=np.array([f"{k}={x}" for k, x in v.items()]), **save)
+
+    if truth:
+        for m in list(ref_sizes) + list(lean_sizes):
+            nth = len(save[f"lml_{m}"])
+            tl, tg, ta = np.zeros(nth), np.zeros((nth, 3)), np.zeros((nth, m))
+            for k in range(nth):
+                t0 = time.time()
+                tl[k], tg[k], ta[k] = orc.ld_truth(save[f"t_{m}"], save[f"y_{m}"], thetas[k])
+                print(f"[truth] m={m} k={k} lml={tl[k]!r} ref_err={abs(tl[k]-save[f'lml_{m}'][k])/abs(tl[k]):.2e} "
+                      f"grad_err={np.abs(tg[k]-save[f'grad_{m}'][k]).max()/np.abs(tg[k]).max():.2e} "
+                      f"alpha_err={np.abs(ta[k]-save[f'alpha_{m}'][k]).max()/np.abs(ta[k]).max():.2e} "
+                      f"({time.time()-t0:.1f}s)", flush=True)
+                save[f"truth_lml_{m}"], save[f"truth_grad_{m}"], save[f"truth_alpha_{m}"] = tl, tg, ta
+                np.savez_compressed(path, versions=np.array([f"{k2}={x}" for k2, x in v.items()]), **save)
+
+
 ALL = dict(
     fixed=lambda: make_fixed_theta(),
+    large=lambda: make_fixed_theta_large(),
     seird=lambda: make_config("seird_090_090_10_360", data_seird),
     heat=lambda: make_config("heat_1_20_05_80_5", data_heat),
     euler=lambda: make_config("euler_006_200_03_400_6", data_euler),
@@ -257,7 +366,7 @@ ALL = dict(
 if __name__ == "__main__":
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     os.chdir("/tmp")
-    names = sys.argv[1:] or list(ALL)
+    names = sys.argv[1:] or [n for n in ALL if n != "large"]   # 'large' takes ~1 h: ask for it by name
     for n in names:
         t0 = time.time()
         ALL[n]()
