@@ -24,11 +24,42 @@ REAL_CONFIGS = ("seird_090_090_10_360", "heat_1_20_05_80_5", "euler_006_200_03_4
                 "euler_006_050_01_400_6")
 
 
-@pytest.fixture
-def ctx():
-    """Process-wide library context, reset to the reference's RBF kernel family before every test."""
+# ---- achieved parity errors ---------------------------------------------------------------------------------
+# GPU tests record the largest error they saw per quantity; the table is written to gpurun_out/parity_errors.json at
+# the end of the session (and summarised in DESIGN.md), so the slack under every tolerance is known.
+ACHIEVED = {}
+
+
+def record(key, value):
+    value = float(value)
+    if np.isfinite(value):
+        ACHIEVED[key] = max(ACHIEVED.get(key, 0.0), value)
+
+
+def pytest_sessionfinish(session, exitstatus):
+    if not ACHIEVED:
+        return
+    import json
+
+    out = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_errors.json"), "w") as f:
+            json.dump(dict(sorted(ACHIEVED.items())), f, indent=1)
+    except OSError:
+        pass
+
+
+@pytest.fixture(params=["small", "blocked"])
+def ctx(request):
+    """Process-wide library context, reset to the reference's RBF kernel family before every test.  Every GPU test
+    runs twice: with the in-shared small-matrix path enabled for m <= 224 (the default) and with the blocked 128-tile
+    path forced for every size."""
     from gpbo_pkg import pkg
 
     c = pkg.default_context(0)
     c.set_kernel_family(0)
-    return c
+    c.set_small_path(224 if request.param == "small" else 0)
+    c.path = request.param
+    yield c
+    c.set_small_path(224)

@@ -144,3 +144,73 @@ def test_matern_oracle_formulas(twice_nu):
     l_ref, g_ref = gp.lml_grad(th)
     l, g, st = orc.np_lml_grad_matern(t1, y, th, twice_nu)
     assert st == 0 and abs(l - l_ref) <= 1e-12 * abs(l_ref) and rel(g, g_ref) <= 1e-10
+
+
+def test_lean_restatement_equals_full_restatement():
+    """np_lml_grad_lean (used for the m = 16384 golden) against np_lml_grad and the reference goldens."""
+    g = load_golden("fixed_theta_synth")
+    m = 512
+    t, y = g[f"t_{m}"], g[f"y_{m}"]
+    for k, th in enumerate(g["thetas"][:4]):
+        a = orc.np_lml_grad(t, y[0], th)
+        b = orc.np_lml_grad_lean(t, y[0], th, block=200, want_alpha=True)
+        assert a[2] == b[2] == 0
+        assert abs(a[0] - b[0]) <= 1e-13 * abs(a[0])
+        assert rel(b[1], a[1]) <= 1e-12
+        assert abs(b[0] - g[f"lml_{m}"][0, k]) <= 1e-10 * abs(g[f"lml_{m}"][0, k])
+    # all-equal abscissae, chi below one ulp of sigma^2: exact zero pivot -> status 1 like np_lml_grad
+    assert orc.np_lml_grad_lean(np.full(64, 0.5), np.linspace(-1, 1, 64), np.log([1.0, 0.1, 1e-17]))[2] == 1
+
+
+def test_large_golden_is_self_consistent():
+    """fixed_theta_large.npz: the lean restatement agreed with the unmodified reference at m = 4096 when the file was
+    made, and the reference is within cond * eps of the 80-bit truth."""
+    import os
+
+    from conftest import GOLDEN
+
+    if not os.path.isfile(os.path.join(GOLDEN, "fixed_theta_large.npz")):
+        pytest.skip("not generated")
+    g = load_golden("fixed_theta_large")
+    assert np.all(g["lean_vs_reference_rel"] <= 1e-11)
+    for m in g["sizes"]:
+        if f"truth_lml_{m}" not in g.files:
+            continue
+        tl, rl = g[f"truth_lml_{m}"], g[f"lml_{m}"]
+        done = tl != 0.0
+        assert np.all(np.abs(tl[done] - rl[done]) <= 1e-11 * np.abs(tl[done]))
+        cond = g[f"cond_{m}"][done]
+        ea = np.abs(g[f"truth_alpha_{m}"][done] - g[f"alpha_{m}"][done]).max(1) / np.abs(g[f"truth_alpha_{m}"][done]).max(1)
+        assert np.all(ea <= 1e-15 * cond * 10)
+
+
+def test_long_double_truth_matches_numpy():
+    """oracle/lml_ld.c (80-bit) against the FP64 restatement at a size where FP64 is accurate to ~1e-13."""
+    import os
+    import shutil
+    import subprocess
+
+    from conftest import ROOT
+
+    if shutil.which("gcc") is None:
+        pytest.skip("needs gcc")
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, capture_output=True)
+    t, y = orc.synthetic_trajectories(1, 256, seed=3)
+    th = np.log([1.3, 0.08, 2e-3])
+    l, g, a = orc.ld_truth(t, y[0], th)
+    l0, g0, _ = orc.np_lml_grad(t, y[0], th)
+    a0, _ = orc.np_alpha(t, y[0], th)
+    assert abs(l - l0) <= 1e-12 * abs(l0) and rel(g, g0) <= 1e-11 and rel(a, a0) <= 1e-10
+    l, g, a = orc.ld_truth(np.full(16, 0.5), np.linspace(-1, 1, 16), np.log([1.0, 0.1, 1e-25]))
+    assert l == -np.inf and np.all(g == 0)
+
+
+def test_package_workload_equals_the_goldens_generator():
+    from gpbo_pkg import pkg
+
+    t, y = orc.synthetic_trajectories(3, 77, seed=5)
+    t2, y2 = pkg.workload.synthetic_trajectories(3, 77, seed=5)
+    assert np.array_equal(t, t2) and np.array_equal(y, y2)
+    T, Y, bl, starts, gp_of = pkg.workload.fit_workload(3, 77, 4, seed=5)
+    assert T.shape == Y.shape == (3, 77) and starts.shape == (12, 3) and np.all(starts[::4] == 0)
+    assert np.all((starts >= bl[:, 0]) & (starts <= bl[:, 1])) and gp_of.tolist() == [0] * 4 + [1] * 4 + [2] * 4
