@@ -70,8 +70,8 @@ struct gpbo_ctx {
     int sm_count = 0;
     double* h_ns = nullptr; size_t h_ns_cap = 0;      // pinned residual read-back of the Newton-Schulz iteration
     std::vector<cudaEvent_t> ns_events;
-    int small_max = SMALL_MAX;          // training sizes up to this run on the in-shared small-matrix path (0: never)
-    DevBuf sm_counter, sm_starts, sm_theta, sm_fun, sm_ints;
+    int small_max = SMALL_DEFAULT;      // training sizes up to this run on the in-shared small-matrix path (0: never)
+    DevBuf sm_counter, sm_starts, sm_theta, sm_fun, sm_ints, sm_dbg;
     int G_res = 0, m_res = 0;           // shape of the problem resident in t_dev / y_dev (gpbo_problem_upload_host)
     double prof_ms[GPBO_NCLASS] = {0};
     long long prof_n[GPBO_NCLASS] = {0};
@@ -284,6 +284,19 @@ int plan_split(gpbo_ctx* c, cudaStream_t s, const MatArgs& a, int mode, int idx,
     static const int split_min = std::getenv("GPBO_SPLIT_MIN") ? std::max(1, std::atoi(std::getenv("GPBO_SPLIT_MIN"))) : 4;
     int nsplit = (int)std::min<long>(split_max, g_sm_count / units);
     nsplit = std::min(nsplit, nk_max / split_min);
+    if (nsplit < 2 && units <= 4L * g_sm_count) {
+        // between one and a few CTAs per SM the launch is quantised: 256 tiles on 148 SMs take two tile times, 1.73
+        // would do.  Cutting every tile into ns k-chunks takes ceil(units ns / SMs) / ns tile times (4 chunks: 1.75);
+        // pick the ns that minimises that plus ~2 % per chunk for writing / re-reading the partial accumulators.
+        static const bool quant = std::getenv("GPBO_NO_QUANT_SPLIT") == nullptr;
+        double best = (double)((units + g_sm_count - 1) / g_sm_count);
+        int best_ns = 1;
+        for (int ns = 2; quant && ns <= 8 && nk_max / ns >= 2 * split_min; ++ns) {
+            const double cost = (double)((units * ns + g_sm_count - 1) / g_sm_count) / ns + 0.02 * ns;
+            if (cost < 0.97 * best) { best = cost; best_ns = ns; }
+        }
+        nsplit = best_ns;
+    }
     if (nsplit < 2) return GPBO_OK;
     const int chunk = (nk_max + nsplit - 1) / nsplit;
     nsplit = (nk_max + chunk - 1) / chunk;
@@ -404,12 +417,30 @@ int small_resident(gpbo_ctx* c, K kernel, int nt, size_t smem) {
     return per_sm * sm_count(c);
 }
 
+// GPBO_SMALL_DBG=1: per-phase cycle counters of the in-shared kernels, printed to stderr after every launch
+long long* small_dbg_begin(gpbo_ctx* c, cudaStream_t s) {
+    static const bool on = std::getenv("GPBO_SMALL_DBG") != nullptr;
+    if (!on) return nullptr;
+    if (c->sm_dbg.ensure(16 * 8) != cudaSuccess) return nullptr;
+    cudaMemsetAsync(c->sm_dbg.p, 0, 16 * 8, s);
+    return c->sm_dbg.as<long long>();
+}
+void small_dbg_end(gpbo_ctx* c, cudaStream_t s, const char* what, int m) {
+    if (!c->sm_dbg.p || std::getenv("GPBO_SMALL_DBG") == nullptr) return;
+    long long h[16];
+    cudaMemcpyAsync(h, c->sm_dbg.p, sizeof(h), cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    std::fprintf(stderr, "[gpbo small %s m=%d] cycles: fill %lld chol32 %lld panel %lld trailing %lld diaginv %lld "
+                         "blockrows %lld z_alpha %lld traces %lld | optimiser %lld over %lld feeds\n",
+                 what, m, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9]);
+}
+
 // LML (+ gradient) of B pairs, one CTA per pair, one launch.  All pointers device.
 int small_lml_grad_device(gpbo_ctx* c, cudaStream_t s, const double* t, const double* y, int m, const double* theta,
                           const int* gp_of, int B, double* lml, double* grad, int* status) {
     int rc = set_small_attrs();
     if (rc) return rc;
-    SmallProblem pr{t, y, m, small_pad(m)};
+    SmallProblem pr{t, y, m, small_pad(m), small_dbg_begin(c, s)};
     const size_t smem = small_smem_bytes(pr.n);
     const int fam = c->family;
     launch(c, C_SMALL, s, [&] {
@@ -423,6 +454,7 @@ int small_lml_grad_device(gpbo_ctx* c, cudaStream_t s, const double* t, const do
         }
 #undef GPBO_SMALL_LML
     });
+    small_dbg_end(c, s, "lml_grad", m);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(s));
     return GPBO_OK;
@@ -455,7 +487,7 @@ int small_fit_device(gpbo_ctx* c, cudaStream_t s, int G, int m, const double* bo
     int* d_nit = d_nfev + B;
     int* d_st = d_nit + B;
     CUDA_TRY(cudaMemcpyAsync(d_gp, gp.data(), (size_t)B * 4, cudaMemcpyHostToDevice, s));
-    SmallProblem pr{c->t_dev.as<double>(), c->y_dev.as<double>(), m, small_pad(m)};
+    SmallProblem pr{c->t_dev.as<double>(), c->y_dev.as<double>(), m, small_pad(m), small_dbg_begin(c, s)};
     const size_t smem = small_smem_bytes(pr.n);
     const int fam = c->family;
     launch(c, C_SMALL, s, [&] {
@@ -470,6 +502,7 @@ int small_fit_device(gpbo_ctx* c, cudaStream_t s, int G, int m, const double* bo
         }
 #undef GPBO_SMALL_FIT
     });
+    small_dbg_end(c, s, "fit", m);
     CUDA_TRY(cudaGetLastError());
     std::vector<int> h_nfev(B), h_nit(B), h_st(B);
     CUDA_TRY(cudaMemcpyAsync(theta_opt, c->sm_theta.p, (size_t)B * 24, cudaMemcpyDeviceToHost, s));
@@ -594,44 +627,82 @@ int sqrtw_device(gpbo_ctx* c, cudaStream_t s, const double* cov, int G, int n, d
         }
         if (plain_ns) l = 1.0;
         for (int p = 0; p < nb; ++p) { done[p] = 0; prev[p] = HUGE_VAL; if (status) status[w0 + p] = 0; if (iters) iters[w0 + p] = maxit; }
-        // convergence bookkeeping for the residual of iteration `it`; returns whether every matrix is finished
-        auto judge = [&](int it) {
+        // Convergence bookkeeping for the residual of iteration `it`, looked at one iteration late: Y, Z then already
+        // hold iterate it + 1, produced with scaling mu_used.  Only an UNSCALED step (mu = 1) is known to improve a
+        // nearly converged iterate (E_{k+1} = 3/4 E_k^2 + 1/4 E_k^3); a scaled step deliberately moves eigenvalues
+        // near 1 down to the lower bound, so after one nothing is accepted.  Returns whether every matrix is finished
+        // and the largest residual of the still running ones.
+        auto judge = [&](int it, double mu_used, double* worst) {
             const double* resid = c->h_ns + (size_t)it * cap;
             bool all_done = true;
-            if (debug_ns) std::fprintf(stderr, "[gpbo sqrtw] it %d r0 %.6e\n", it, std::sqrt(resid[0]));
+            *worst = 0.0;
+            if (debug_ns) std::fprintf(stderr, "[gpbo sqrtw] it %d r0 %.6e mu %.6f\n", it, std::sqrt(resid[0]), mu_used);
             for (int p = 0; p < nb; ++p) {
                 if (done[p]) continue;
                 const double r = std::sqrt(resid[p]);
                 if (!std::isfinite(r)) {                       // an eigenvalue <= 0 made Z blow up
                     done[p] = 2;
-                } else if (r <= 1e-11 * std::sqrt((double)ld) || (prev[p] < 0.05 && r >= 0.25 * prev[p])) {
-                    // converged; second test: the quadratic phase (r_k ~ r_{k-1}^2) has stalled at the rounding
-                    // floor ~ cond * eps -- the reference's eigh result is no more accurate there
+                } else if (mu_used == 1.0 &&
+                           (0.75 * r * r <= 1e-11 * std::sqrt((double)ld) || (prev[p] < 0.05 && r >= 0.25 * prev[p]))) {
+                    // converged: the next iterate (already in Y, Z) has a residual <= 0.75 r^2; or the quadratic
+                    // phase has stalled at the rounding floor ~ cond * eps -- the reference's eigh result is no
+                    // more accurate there
                     done[p] = 1;
-                    if (iters) iters[w0 + p] = it;
+                    if (iters) iters[w0 + p] = it + 1;
                 }
                 prev[p] = r;
-                if (!done[p]) all_done = false;
+                if (!done[p]) { all_done = false; *worst = std::max(*worst, r); }
             }
             return all_done;
         };
+        auto fmap = [](double mu, double x) { return 0.5 * mu * x * (3.0 - mu * mu * x * x); };
+        double mu_prev = 1.0;
+        // a positive definite input is within ||I - T|| < 1 after about log(1 / l_0) / log(2.6) scaled steps; one whose
+        // residual is still >= 0.9 long after that has an eigenvalue <= 0 (the reference's ValueError case)
+        const int it_hopeless = (int)std::ceil(std::log(1.0 / l) / std::log(2.5)) + 14;
         for (int it = 0; it < maxit; ++it) {
             launch(c, C_SQRTW, s, [&] { ns_gemm_kernel<<<dim3(nb * nfull, 1), NTHR, MAIN_SMEM, s>>>(a, nfull, 0, 0.0, 0.0); });
             launch(c, C_SQRTW, s, [&] { ns_resid_kernel<<<nb, NTHR, 0, s>>>(a.part, nfull, c->nsResid.as<double>()); });
             CUDA_TRY(cudaMemcpyAsync(c->h_ns + (size_t)it * cap, c->nsResid.p, (size_t)nb * 8, cudaMemcpyDeviceToHost, s));
             CUDA_TRY(cudaEventRecord(c->ns_events[it], s));
-            if (it >= 1) {
+            // The first residual is waited for: it decides whether the input needs scaling at all (a well conditioned
+            // matrix must not have its eigenvalues near 1 thrown down by a scaled step).  Afterwards the residuals are
+            // read ONE iteration late, when the next product is already enqueued: the host never drains the queue.
+            double worst = 0.0;
+            if (it == 0) {
+                CUDA_TRY(cudaEventSynchronize(c->ns_events[0]));
+                for (int p = 0; p < nb; ++p) {
+                    const double r = std::sqrt(c->h_ns[p]);
+                    worst = std::isfinite(r) ? std::max(worst, r) : HUGE_VAL;
+                }
+                // spectrum of T_0 within [1 - r, 1 + r] (r = Frobenius norm of I - T): x >= sqrt(1 - r)
+                if (worst < 1.0) l = std::max(l, std::sqrt(1.0 - worst));
+            } else {
                 CUDA_TRY(cudaEventSynchronize(c->ns_events[it - 1]));
-                if (judge(it - 1)) break;          // Y, Z already hold the (further improved) iterate `it`
+                if (judge(it - 1, mu_prev, &worst)) break;    // Y, Z hold iterate `it`: one unscaled step past it - 1
+                if (it > it_hopeless && worst >= 0.9) {
+                    for (int p = 0; p < nb; ++p)
+                        if (!done[p]) done[p] = 2;
+                    break;
+                }
+                // x_{it-1} in [sqrt(1 - r), sqrt(1 + r)] -> after the step with mu_prev: x_it >= min of the images
+                if (worst < 1.0) {
+                    const double lo = std::min(fmap(mu_prev, std::sqrt(1.0 - worst)),
+                                               fmap(mu_prev, std::min(1.0, std::sqrt(1.0 + worst))));
+                    if (std::isfinite(lo)) l = std::max(l, std::min(1.0, lo));
+                }
             }
-            if (it == maxit - 1) {
+            if (it == maxit - 1) {                            // out of iterations: the last residual decides directly
                 CUDA_TRY(cudaEventSynchronize(c->ns_events[it]));
-                judge(it);
+                const double* resid = c->h_ns + (size_t)it * cap;
+                for (int p = 0; p < nb; ++p)
+                    if (!done[p] && std::sqrt(resid[p]) <= 1e-11 * std::sqrt((double)ld)) done[p] = 1;
                 break;
             }
-            const double mu = std::sqrt(3.0 / (1.0 + l + l * l));
+            const double mu = (plain_ns || l > 1.0 - 1e-3) ? 1.0 : std::sqrt(3.0 / (1.0 + l + l * l));
             const double ca = 1.5 * mu, cb = 0.5 * mu * mu * mu;
-            l = std::min(1.0, 0.5 * mu * l * (3.0 - mu * mu * l * l));
+            l = std::min(1.0, fmap(mu, l));
+            mu_prev = mu;
             launch(c, C_SQRTW, s, [&] { ns_gemm_kernel<<<dim3(nb * ntiles, 2), NTHR, MAIN_SMEM, s>>>(a, ntiles, 1, ca, cb); });
             std::swap(a.Y, a.Yn);
             std::swap(a.Z, a.Zn);
@@ -678,7 +749,7 @@ int gpbo_destroy(gpbo_ctx* c) {
                       &c->X, &c->trow, &c->tsrc, &c->out1, &c->out2, &c->cov_dev,
                       &c->nsY, &c->nsZ, &c->nsT, &c->nsTT, &c->nsYn, &c->nsZn, &c->nsPart, &c->nsNorm, &c->nsResid, &c->w_dev,
                       &c->pre, &c->wp_lhs, &c->wp_rhs, &c->wp_olhs, &c->wp_orhs,
-                      &c->sm_counter, &c->sm_starts, &c->sm_theta, &c->sm_fun, &c->sm_ints};
+                      &c->sm_counter, &c->sm_starts, &c->sm_theta, &c->sm_fun, &c->sm_ints, &c->sm_dbg};
     for (DevBuf* b : bufs) b->release();
     for (auto& r : c->recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);

@@ -28,6 +28,7 @@
 namespace gpbo {
 
 constexpr int SMALL_MAX = 224;     // largest training size of the in-shared path
+constexpr int SMALL_DEFAULT = 96;  // sizes up to this take it by default (measured crossover with the blocked path)
 constexpr int SB = 32;             // panel / block width
 
 __host__ __device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
@@ -40,7 +41,28 @@ struct SmallProblem {
     const double* y;   // [G][m]
     int m;             // valid size
     int n;             // m rounded up to a multiple of 32
+    long long* dbg;    // nullptr, or 16 counters: clock cycles of thread 0 per phase, summed over all CTAs (GPBO_SMALL_DBG)
 };
+
+// phase timing for tuning runs (GPBO_SMALL_DBG=1): thread 0 accumulates the cycles since the previous mark
+struct SmallClock {
+    long long* dbg;
+    long long last;
+};
+__device__ __forceinline__ long long small_now() {
+#ifdef __CUDA_ARCH__
+    return clock64();
+#else
+    return 0;
+#endif
+}
+__device__ __forceinline__ void small_mark(SmallClock& c, int phase) {
+    if (c.dbg && threadIdx.x == 0) {
+        const long long now = small_now();
+        atomicAdd(reinterpret_cast<unsigned long long*>(c.dbg + phase), (unsigned long long)(now - c.last));
+        c.last = now;
+    }
+}
 
 struct SmallBox { double lo[3], hi[3]; };
 
@@ -148,6 +170,7 @@ __device__ void small_eval(const SmallProblem& pr, int gp, double th0, double th
     double* dinv = z + n;
     double* red = dinv + n;                       // 64 doubles
 
+    SmallClock clk{pr.dbg, pr.dbg ? small_now() : 0};
     const double sig2 = exp(th0), ell = exp(th1), chi = exp(th2);
     for (int i = tid; i < n; i += NT) {
         x[i] = i < m ? pr.t[(long)gp * m + i] / ell : 0.0;        // kernels.py:1559 (X / length_scale)
@@ -170,12 +193,14 @@ __device__ void small_eval(const SmallProblem& pr, int gp, double th0, double th
         }
     }
     __syncthreads();
+    small_mark(clk, 0);
 
     // 2. Cholesky, right-looking with 32-wide panels
     bool bad = false;
     for (int kb = 0; kb < nblk; ++kb) {
         const int o = kb * SB;
         bad |= small_chol32<NT>(L, o, dinv, red);
+        small_mark(clk, 1);
         const int R0 = o + SB, nb = n - R0;
         if (nb <= 0) break;
         // panel: X L_kk^T = A by forward substitution, one thread per row (row in registers, L_kk broadcast)
@@ -200,6 +225,7 @@ __device__ void small_eval(const SmallProblem& pr, int gp, double th0, double th
             for (int c = 0; c < SB; ++c) Ar[c] = xr[c];
         }
         __syncthreads();
+        small_mark(clk, 2);
         // trailing update of the lower triangle: A[r][c] -= sum_k X[r][k] X[c][k], 6 x 6 register tiles
         for (int rc0 = 0; rc0 < nb; rc0 += CR)
             for (int cc0 = 0; cc0 < rc0 + CR && cc0 < nb; cc0 += 96) {
@@ -235,6 +261,7 @@ __device__ void small_eval(const SmallProblem& pr, int gp, double th0, double th
                     }
             }
         __syncthreads();
+        small_mark(clk, 3);
     }
     if (bad) {                                    // uniform: every thread saw the same pivots
         if (tid == 0) { out[0] = -INFINITY; out[1] = 0.0; out[2] = 0.0; out[3] = 0.0; *st = 1; }
@@ -265,6 +292,7 @@ __device__ void small_eval(const SmallProblem& pr, int gp, double th0, double th
             if (rr >= jc) L[tri(o + rr) + o + jc] = w[rr];
     }
     __syncthreads();
+    small_mark(clk, 4);
     // 3b. block rows: W_i,: = -W_ii (L_i,: W_<i,<i), both products with 2 x 12 (RI x JJ) register tiles
     for (int bi = 1; bi < nblk; ++bi) {
         const int o = bi * SB;
@@ -329,6 +357,7 @@ __device__ void small_eval(const SmallProblem& pr, int gp, double th0, double th
         __syncthreads();
     }
 
+    small_mark(clk, 5);
     // 4. z = W y (a warp per row), alpha = W^T z (a thread per column)
     for (int i = warp; i < n; i += NW) {
         const double* Wi = L + tri(i);
@@ -352,6 +381,7 @@ __device__ void small_eval(const SmallProblem& pr, int gp, double th0, double th
     }
     __syncthreads();
 
+    small_mark(clk, 6);
     // 5. K^-1 = W^T W in 6 x 6 register tiles fused with the gradient traces; 6. LML
     double s[5] = {0.0, 0.0, 0.0, 0.0, 0.0};     // s0, s1, s2, y'alpha, sum log L_ii
     for (int rc0 = 0; rc0 < n; rc0 += CR)
@@ -414,6 +444,7 @@ __device__ void small_eval(const SmallProblem& pr, int gp, double th0, double th
         *st = ok ? 0 : 1;
     }
     __syncthreads();
+    small_mark(clk, 7);
 }
 
 // Fixed-theta entry: one CTA per pair.
@@ -461,8 +492,13 @@ small_fit_kernel(SmallProblem pr, const double* __restrict__ starts, const int* 
         for (;;) {
             small_eval<NT, FAM>(pr, gp, s_theta[0], s_theta[1], s_theta[2], sm, s_out, &s_st);
             if (threadIdx.x == 0) {
+                const long long c0 = pr.dbg ? small_now() : 0;
                 double gneg[3] = {-s_out[1], -s_out[2], -s_out[3]};
                 opt.feed(-s_out[0], gneg);        // obj_func = (-lml, -grad), _gpr.py:300-307
+                if (pr.dbg) {
+                    atomicAdd(reinterpret_cast<unsigned long long*>(pr.dbg + 8), (unsigned long long)(small_now() - c0));
+                    atomicAdd(reinterpret_cast<unsigned long long*>(pr.dbg + 9), 1ULL);
+                }
                 s_run = opt.running() ? 1 : 0;
                 s_theta[0] = opt.x[0]; s_theta[1] = opt.x[1]; s_theta[2] = opt.x[2];
             }

@@ -104,12 +104,11 @@ def test_posterior_moments_at_m4096(ctx):
 @pytest.mark.parametrize("m", [1, 2, 10, 31, 32, 33, 50, 64, 65, 90, 120, 160, 200, 223, 224])
 def test_small_path_lml_grad(ctx, m):
     """Every padding case of the in-shared path (n = 32 ... 224, both CTA shapes) against the oracle, batch of pairs
-    over several GPs, including a not-positive-definite pair in the middle of the batch."""
+    over several GPs (the not-positive-definite status is covered by test_not_positive_definite_status on both paths)."""
     t, y = orc.synthetic_trajectories(3, m, seed=100 + m)
     T = np.tile(t, (3, 1))
     rng = np.random.default_rng(m)
     theta = np.log(np.array([1.2, 0.15, 1e-2]))[None, :] + 0.4 * rng.standard_normal((9, 3))
-    theta[4] = np.log([1.0, 50.0, 1e-17]) if m > 2 else theta[4]       # rank-one K, chi below one ulp: not PD
     gp_of = (np.arange(9) % 3).astype(np.int32)
     lml, grad, st = ctx.lml_grad(T, y, theta, gp_of)
     for k in range(9):
