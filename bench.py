@@ -201,8 +201,11 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return float(tt.item())
 
-    # FP64 tensor-pipe peak (DMMA issue rate), measured live: MEASURED_PEAKS.json has no FP64 entry
-    dmma_peak, _ = ctx.dmma_peak(100000)
+    # FP64 tensor-pipe peak (DMMA issue rate), measured live: MEASURED_PEAKS.json has no FP64 entry.  Best of five
+    # ~60 ms runs after a warm-up run (the first launch on a cold GPU sees ramping clocks and reads ~2 % low).
+    ctx.dmma_peak(100000)
+    dmma_runs = [ctx.dmma_peak(100000)[0] for _ in range(5)]
+    dmma_peak = max(dmma_runs)
 
     # ---- warm-up: W rounds of one wave of pairs (kernels loaded, workspace allocated, clocks up) -------------------
     ctx.upload_problem(T, Y)
@@ -282,6 +285,9 @@ def main():
         "frac": achieved / dmma_peak, "traffic": traffic,
         "peak_source": "FP64 DMMA issue-rate micro-benchmark run in this process (gpbo_bench_dmma_peak); "
                        "MEASURED_PEAKS.json holds no FP64 figure; cuBLAS DGEMM rate beside it in dgemm_cublas_tflops",
+        "peak_runs": [round(x, 3) for x in dmma_runs],
+        "peak_arithmetic": 128e-12 * torch.cuda.get_device_properties(dev).multi_processor_count
+                           * (clocks.get("sm_max_mhz") or 0.0) * 1e6,
         "flops_per_launch": total_flops_dom / launches_dom, "avg_launch_ms": dom_ms / launches_dom,
         "share_of_step": prof[dom][0] / max(kernel_total_ms, 1e-9),
         "whole_eval_tflops": evals * float(m) ** 3 / (ms * 1e-3) / 1e12,
@@ -289,6 +295,10 @@ def main():
         "kernel_time_share_of_wall": kernel_total_ms / max(e0.elapsed_time(e1), 1e-9),
         "dmma_issued_tflops": {k: issued_pp[k] * local_evals / (prof[k][0] * 1e-3) / 1e12
                                for k in issued_pp if prof[k][0] > 0},
+        "class_frac_algorithmic": {
+            "potrf": flops_third * local_evals / (max(prof["chol_diag"][0] + prof["chol_panel"][0], 1e-9) * 1e-3) / 1e12 / dmma_peak,
+            "trtri": flops_third * local_evals / (max(prof["trtri"][0], 1e-9) * 1e-3) / 1e12 / dmma_peak,
+            "lauum_grad": flops_third * local_evals / (max(prof["lauum_grad"][0], 1e-9) * 1e-3) / 1e12 / dmma_peak},
         "kernel_ms": {k: round(v[0], 3) for k, v in prof.items() if v[1]},
         "rank": rank,
     }
