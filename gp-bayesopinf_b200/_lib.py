@@ -15,9 +15,9 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgpbo.so")
 
-NCLASS = 13
+NCLASS = 14
 KERNEL_CLASSES = ("prep", "chol_diag", "chol_panel", "trsv", "trtri", "lauum_grad", "finalize",
-                  "cross_panel", "schur", "mean_std", "assemble", "sqrtw", "small")
+                  "cross_panel", "schur", "mean_std", "assemble", "sqrtw", "small", "std")
 
 EXPORTS = (
     "gpbo_version", "gpbo_last_error", "gpbo_create", "gpbo_destroy", "gpbo_launch_count",

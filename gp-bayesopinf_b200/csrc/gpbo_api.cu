@@ -80,7 +80,7 @@ struct gpbo_ctx {
     // per-call device copies of host inputs / outputs
     DevBuf t_dev, y_dev, ypad, theta_dev, gpof_dev, lml_dev, grad_dev, st_dev;
     // prediction
-    DevBuf X, trow, tsrc, out1, out2, cov_dev;
+    DevBuf X, trow, tsrc, out1, out2, cov_dev, sweep_flags, kzz_tab, kzz_flag;
     // sqrtW (Newton-Schulz)
     DevBuf nsY, nsZ, nsT, nsTT, nsYn, nsZn, nsPart, nsNorm, nsResid, w_dev;
     int w_G = 0, w_n = 0;            // shape of the sqrtW stack currently resident in w_dev
@@ -94,7 +94,7 @@ struct gpbo_ctx {
 
 namespace {
 
-enum { C_PREP = 0, C_DIAG, C_PANEL, C_TRSV, C_TRTRI, C_LAUUM, C_FINAL, C_CROSS, C_SCHUR, C_MEAN, C_ASM, C_SQRTW, C_SMALL };
+enum { C_PREP = 0, C_DIAG, C_PANEL, C_TRSV, C_TRTRI, C_LAUUM, C_FINAL, C_CROSS, C_SCHUR, C_MEAN, C_ASM, C_SQRTW, C_SMALL, C_STD };
 
 template <class F>
 inline void launch(gpbo_ctx* c, int cls, cudaStream_t s, F&& f) {
@@ -257,6 +257,7 @@ int set_kernel_attrs() {
     CUDA_TRY(cudaFuncSetAttribute(chol_panel_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(chol_panel_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(trtri_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(cross_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(splitk_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(lauum_grad_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
@@ -832,9 +833,13 @@ static int assemble_impl(gpbo_ctx* c, int fam, int kind, const double* t1, long 
         const int nt = (n1 + SYM_T - 1) / SYM_T;
         dim3 gs(nt * (nt + 1) / 2, B);
         dim3 gg((n2 + ASM_COLS - 1) / ASM_COLS, (n1 + ASM_ROWS - 1) / ASM_ROWS, B);
+        // short second dimension: the flat kernel (one contiguous array, every thread busy whatever n2 is)
+        const bool flat = !sym && n2 >= FLAT_MIN_N2 && n2 <= FLAT_MAX_N2;
+        dim3 gf((unsigned)((os + FLAT_E - 1) / FLAT_E), B);
 #define GPBO_ASM_CASE(F, K)                                                                                              \
     case K:                                                                                                              \
         if (sym) assemble_sym_kernel<F, K><<<gs, NTHR, SYM_SMEM, s>>>(t1, t1_stride, n1, theta, out, os);                \
+        else if (flat) assemble_flat_kernel<F, K><<<gf, NTHR, 0, s>>>(t1, t1_stride, n1, t2, t2_stride, n2, theta, out, os); \
         else assemble_general_kernel<F, K><<<gg, NTHR, 0, s>>>(t1, t1_stride, n1, t2, t2_stride, n2, theta, out, os);    \
         break;
 #define GPBO_ASM_FAM(F)                                                                                                  \
@@ -1227,23 +1232,50 @@ static int moments_device(gpbo_ctx* c, cudaStream_t s, int mode, const double* t
             CrossArgs crx = cr;
             crx.kind = mode == 0 ? 0 : 2;
             const long xs = (long)n_pad * m_pad;
-            for (int j = 0; j < a.T; ++j) {
-                PreAcc pre;
-                rc = plan_split(c, s, a, 2, j, nb, xT, j * (TB / BK), c->X.as<double>(), xs, &pre);
-                if (rc) return rc;
+            const int units = nb * xT;
+            static const bool no_sweep = std::getenv("GPBO_NO_SWEEP") != nullptr;
+            if (!no_sweep && 2 * units >= sm_count(c)) {
+                // enough row tiles to fill the GPU: one persistent launch, the sweeps cut into equal cost ranges
+                CUDA_TRY(c->sweep_flags.ensure((size_t)units * 4));
+                CUDA_TRY(cudaMemsetAsync(c->sweep_flags.p, 0, (size_t)units * 4, s));
+                const int grid = std::min(units, sm_count(c));
                 launch(c, C_CROSS, s, [&] {
-                    chol_panel_kernel<0, true><<<nb * xT, NTHR, TILE_SMEM, s>>>(a, j, c->X.as<double>(), xs, xT, crx, pre);
+                    cross_sweep_kernel<<<grid, NTHR, TILE_SMEM, s>>>(a, c->X.as<double>(), xs, xT, units, crx,
+                                                                     c->sweep_flags.as<int>());
                 });
+            } else {
+                for (int j = 0; j < a.T; ++j) {
+                    PreAcc pre;
+                    rc = plan_split(c, s, a, 2, j, nb, xT, j * (TB / BK), c->X.as<double>(), xs, &pre);
+                    if (rc) return rc;
+                    launch(c, C_CROSS, s, [&] {
+                        chol_panel_kernel<0, true><<<nb * xT, NTHR, TILE_SMEM, s>>>(a, j, c->X.as<double>(), xs, xT, crx, pre);
+                    });
+                }
             }
             if (mode == 0) {
-                launch(c, C_MEAN, s, [&] {
+                launch(c, C_STD, s, [&] {
                     std_kernel<<<mgrid, NTHR, 0, s>>>(a, c->X.as<double>(), xs, n, out2 + (size_t)w0 * n, n);
                 });
             } else {
                 const int ntiles = xT * (xT + 1) / 2;
+                // N2: equispaced estimation points -> K_zz from a per-GP table of m' values indexed by the lag
+                static const bool no_toeplitz = std::getenv("GPBO_NO_TOEPLITZ") != nullptr;
+                double* ktab = nullptr;
+                int* kflag = nullptr;
+                if (!no_toeplitz) {
+                    CUDA_TRY(c->kzz_tab.ensure((size_t)cap * n_pad * 8));
+                    CUDA_TRY(c->kzz_flag.ensure((size_t)cap * 4));
+                    ktab = c->kzz_tab.as<double>();
+                    kflag = c->kzz_flag.as<int>();
+                    launch(c, C_PREP, s, [&] {
+                        kzz_table_kernel<<<nb, NTHR, 0, s>>>(trow_src + (size_t)w0 * src_stride, src_stride, crx,
+                                                             c->pp.as<PairParams>(), ktab, kflag);
+                    });
+                }
                 launch(c, C_SCHUR, s, [&] {
                     schur_kernel<<<nb * ntiles, NTHR, MAIN_SMEM, s>>>(a, c->X.as<double>(), xs, crx, ntiles,
-                                                                      cov + (size_t)w0 * n * n, (long)n * n);
+                                                                      cov + (size_t)w0 * n * n, (long)n * n, ktab, kflag);
                 });
             }
         }

@@ -129,62 +129,92 @@ __global__ void prep_pairs_kernel(const double* __restrict__ theta, const int* _
 // Returns (to every thread) whether a non-positive pivot was met; *logsum gets sum_i log L_ii.
 //
 // Blocked right-looking algorithm with 32-wide panels:
-//   per panel  (1) chol32_block: the 32x32 diagonal block is factored by all threads (32 rank-1 steps, one
-//                  barrier each);
+//   per panel  (1) chol32_block: the 32x32 diagonal block is factored by one warp in registers (warp_chol32:
+//                  shuffles, no barrier);
 //              (2) panel X L_kk^T = A by forward substitution, one thread per row with the row in registers;
 //              (3) all warps: trailing A22 -= X X^T (register tiles);
 //   then the four 32x32 diagonal blocks are inverted concurrently (2 lanes per column), and the off-diagonal
 //   blocks of inv(L) follow by block rows: W_ij = -W_ii * sum_k L_ik W_kj.
-// `scratch` needs PB doubles during the factorisation and PB*(3*PB+1) during the inversion (re-used).
+// `scratch` needs PB + 1 doubles during the factorisation and PB*(3*PB+1) during the inversion (re-used).
 constexpr int PB = 32;            // panel width
 constexpr int LDG = 3 * PB + 1;   // stride of the G scratch of the inversion
 constexpr int POTF_SCRATCH = PB * LDG;
 
-// All 256 threads: Cholesky of the 32x32 block at P[o..o+32)^2 (lower part, in place); dinv[o+i] = 1 / L_ii.
-// `rsv` = PB doubles of scratch.  Returns (uniformly) whether a pivot was <= 0.
-//
-// Right-looking with unscaled columns (the column scaling by 1/sqrt(d_j) is applied once at the end), so a
-// step is: broadcast pivot -> reciprocal -> rank-1 update of <= 496 entries by 256 threads -> one barrier.
-__device__ __forceinline__ bool chol32_block(double* P, int o, double* dinv, double* rsv) {
-    const int tid = threadIdx.x;
-    const int r = tid >> 3, c8 = tid & 7;                 // row of the block, column class
-    double* Pr = P + (o + r) * LDP + o;
+// Reciprocal from the hardware approximation plus two Newton steps (<= 1 ulp): the one long-latency operation on the
+// critical path of a pivot step.
+__device__ __forceinline__ double fast_rcp(double d) {
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+    double e = fma(-d, x, 1.0);
+    x = fma(x, e, x);
+    e = fma(-d, x, 1.0);
+    return fma(x, e, x);
+}
+
+// ONE WARP factors a 32 x 32 symmetric positive definite block in place: lane r takes row r into registers
+// (a[c] = A[r][c], c <= r).  Right-looking with unscaled columns; per pivot step: the pivot comes by shuffle from
+// lane j (so its reciprocal starts at once), the lanes publish their column-j entries in a double-buffered 32-double
+// shared array and read the multipliers a_cj back as broadcasts, rank-1 update in registers -- warp-synchronous, one
+// __syncwarp per step, no CTA-wide barrier (the all-threads version this replaces spent ~21 000 cycles per block on
+// its 32 barriers).  The 32 square roots are taken once at the end.
+// rowp: this lane's row (first of the block's 32 columns); dinv_lane receives 1 / L_rr.  Returns (warp-uniformly)
+// whether a pivot was <= 0 (the pivot is then replaced by 1).  Not inlined: its 32-double register row must not
+// inflate the register allocation of the DMMA kernels that call it.
+__device__ __noinline__ bool warp_chol32(double* rowp, double* dinv_lane) {
+    __shared__ __align__(16) double colbuf[2][32];
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    // Nothing below is predicated on (c <= lane): the registers a[c], c > lane, hold whatever lies right of the
+    // diagonal (finite or not) and are updated like the rest, but never read by another lane (col[c] is only read for
+    // rows c > j, from lane c's VALID entry a[j], j < c) and never written back.  32 x 31 / 2 unpredicated DFMAs and 16-byte
+    // broadcast loads instead of 4700 instructions of predicate bookkeeping.
+    double a[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) a[c] = rowp[c];
+    double my_d = 1.0;
     bool bad = false;
-    for (int j = 0; j < PB - 1; ++j) {
-        double d = P[(o + j) * LDP + o + j];
-        if (!(d > 0.0)) { bad = true; d = 1.0; }
-        const double inv_d = __drcp_rn(d);                 // the only long-latency op on the step's critical path
-        if (tid == 0) rsv[j] = d;
-        if (r > j) {
-            const double w = Pr[j] * inv_d;
 #pragma unroll
-            for (int q = 0; q < PB / 8; ++q) {
-                const int c = c8 + 8 * q;
-                if (c > j && c <= r) Pr[c] = fma(-w, P[(o + c) * LDP + o + j], Pr[c]);
-            }
-        }
-        __syncthreads();
-    }
-    {
-        double d = P[(o + PB - 1) * LDP + o + PB - 1];
+    for (int j = 0; j < 32; ++j) {
+        double d = __shfl_sync(FULL, a[j], j);
+        double* col = colbuf[j & 1];
+        col[lane] = a[j];
+        __syncwarp();
         if (!(d > 0.0)) { bad = true; d = 1.0; }
-        if (tid == 0) rsv[PB - 1] = d;
-    }
-    __syncthreads();
-    if (tid < PB) rsv[tid] = rsqrt(rsv[tid]);              // all 32 square roots at once
-    __syncthreads();
-    // scale: L_rc = a_rc * rs_c (c < r), L_cc = d_c * rs_c
-#pragma unroll
-    for (int q = 0; q < PB / 8; ++q) {
-        const int c = c8 + 8 * q;
-        if (c <= r) {
-            const double v = Pr[c];
-            Pr[c] = (c == r && !(v > 0.0)) ? 1.0 : v * rsv[c];
+        if (lane == j) my_d = d;
+        const double w = -(a[j] * fast_rcp(d));
+        if ((j + 1) & 1) {                               // odd first column: one scalar step, then aligned pairs
+            if (j + 1 < 32) a[j + 1] = fma(w, col[j + 1], a[j + 1]);
         }
+#pragma unroll
+        for (int c = (j + 2) & ~1; c < 32; c += 2) {
+            const double2 cc = *reinterpret_cast<const double2*>(col + c);
+            a[c] = fma(w, cc.x, a[c]);
+            a[c + 1] = fma(w, cc.y, a[c + 1]);
+        }
+        // no second barrier: step j + 1 writes the other buffer, and nobody reaches step j + 2's write before every
+        // lane has passed step j + 1's __syncwarp, i.e. finished reading this one
     }
-    if (tid < PB) dinv[o + tid] = rsv[tid];               // 1 / L_ii = rs_i  (L_ii = d_i rs_i = sqrt(d_i))
-    __syncthreads();
+    const double rs = rsqrt(my_d);
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+        const double rsc = __shfl_sync(FULL, rs, c);
+        if (c <= lane) rowp[c] = (c == lane ? my_d : a[c]) * rsc;
+    }
+    *dinv_lane = rs;
+    __syncwarp();
     return bad;
+}
+
+// Cholesky of the 32x32 block at P[o..o+32)^2 (lower part, in place, row stride LDP) by warp 0; dinv[o+i] = 1 / L_ii.
+// `flag` = one double of scratch.  Ends with __syncthreads(); returns (uniformly) whether a pivot was <= 0.
+__device__ __forceinline__ bool chol32_block(double* P, int o, double* dinv, double* flag) {
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        const bool bad = warp_chol32(P + (o + lane) * LDP + o, dinv + o + lane);
+        if (lane == 0) *flag = bad ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    return *flag != 0.0;
 }
 
 // nv = number of valid (non-padding) rows of the block: rows >= nv are identity rows (the reference's sizes
@@ -266,30 +296,29 @@ __device__ __forceinline__ bool potf2_trtri_smem(double* P, double* scratch, dou
         }
         __syncthreads();
     }
-    // inverses of the four 32x32 diagonal blocks, all at once: 64 threads per block, 2 lanes per column jc,
-    // forward substitution over the rows; W is written transposed into the strict upper part of P, where the
-    // column under construction is contiguous.
-    if ((tid >> 6) < nvb) {                            // whole warps: 64 threads per diagonal block
-        const int o = (tid >> 6) * PB, jc = (tid & 63) >> 1, h = tid & 1;
-        double* Wc = P + (o + jc) * LDP + o;           // Wc[k] = W[k][jc], k > jc
-        const double wjj = dinv[o + jc];
-        for (int rr = 1; rr < PB; ++rr) {
+    // inverses of the 32x32 diagonal blocks, all at once: one warp per block, lane = column jc with the column in
+    // registers (forward substitution over the rows, L_bb read as broadcasts); W is written transposed into the strict
+    // upper part of P, where the column under construction is contiguous.
+    if (warp < nvb) {
+        const int o = warp * PB, jc = lane;
+        double w[PB];
+#pragma unroll
+        for (int rr = 0; rr < PB; ++rr) {
+            const double* Lr = P + (o + rr) * LDP + o;
             double s0 = 0.0, s1 = 0.0;
-            if (rr > jc) {
-                const double* Lr = P + (o + rr) * LDP + o;
-                if (h == 0) s0 = Lr[jc] * wjj;
-                int k = jc + 1 + h;
-                for (; k + 2 < rr; k += 4) {
-                    s0 = fma(Lr[k], Wc[k], s0);
-                    s1 = fma(Lr[k + 2], Wc[k + 2], s1);
-                }
-                if (k < rr) s0 = fma(Lr[k], Wc[k], s0);
+#pragma unroll
+            for (int k = 0; k + 1 < rr; k += 2) {
+                s0 = fma(Lr[k], w[k], s0);            // w[k] = 0 for k < jc
+                s1 = fma(Lr[k + 1], w[k + 1], s1);
             }
-            double sacc = s0 + s1;
-            sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
-            if (h == 0 && rr > jc) Wc[rr] = -sacc * dinv[o + rr];
-            __syncwarp();
+            if (rr & 1) s0 = fma(Lr[rr - 1], w[rr - 1], s0);
+            const double di = dinv[o + rr];
+            w[rr] = rr < jc ? 0.0 : (rr == jc ? di : -(s0 + s1) * di);
         }
+        double* Wc = P + (o + jc) * LDP + o;           // Wc[k] = W[k][jc], k > jc
+#pragma unroll
+        for (int rr = 1; rr < PB; ++rr)
+            if (rr > jc) Wc[rr] = w[rr];
     }
     __syncthreads();
     // off-diagonal blocks of W = inv(L), block row bi; W stored transposed in the strict upper part of P
@@ -537,6 +566,9 @@ chol_panel_kernel(MatArgs a, int j, double* X, long x_stride, int xT, CrossArgs 
 
     double* S = smem;
     double* stages = smem + TB * LDS;
+    const double* Dj = a.D + ((long)p * a.T + j) * (TB * TB);
+    __syncthreads();   // every warp is done with the main loop's ring: its memory becomes S + the epilogue's stages
+    epi_prefill_D(Dj, stages, ring, tc);   // inv(L_jj) slices fly while the K tile is generated in registers
     {
         const PairParams q = a.pp[p];
         double xr[8], xc[4][2];
@@ -559,13 +591,11 @@ chol_panel_kernel(MatArgs a, int j, double* X, long x_stride, int xT, CrossArgs 
                     acc.v[mi][ni][e] = kv - acc.v[mi][ni][e];
                 }
     }
-    __syncthreads();   // ring memory is re-used for S
     acc_to_smem<LDS>(acc, S, tc);
     __syncthreads();
     Acc out;
     acc_zero(out);
-    const double* Dj = a.D + ((long)p * a.T + j) * (TB * TB);
-    epi_product_SxDt(out, S, Dj, stages, ring, tc);
+    epi_product_SxDt(out, S, Dj, stages, ring, tc, true);
     double* dst = Xp + (long)i * TB * a.lda + j * TB;
 #pragma unroll
     for (int mi = 0; mi < 8; ++mi)
@@ -574,6 +604,113 @@ chol_panel_kernel(MatArgs a, int j, double* X, long x_stride, int xT, CrossArgs 
             double2 v = make_double2(out.v[mi][ni][0], out.v[mi][ni][1]);
             *reinterpret_cast<double2*>(dst + (long)tc.row(mi) * a.lda + tc.col(ni, 0)) = v;
         }
+}
+
+// ---- prediction TRSM as ONE persistent launch ("row sweep") ---------------------------------
+// Row tile i of X = K_* L^-T depends only on itself and on L:  X_ij = (S_ij - sum_{k<j} X_ik L_jk^T) inv(L_jj)^T,
+// so a CTA can sweep j = 0 .. T-1 for its 128 rows with no other CTA involved.  A unit = one (GP, row tile) sweep;
+// all units cost the same, so with `units` not a multiple of the CTA count (8 GPs x 32 row tiles = 256 units on 148
+// SMs) whole-unit scheduling loses up to half a round.  The sweeps are therefore cut ALONG j: the linear work order
+// (unit-major, step-minor, step j costing 2 j + 2) is divided into gridDim.x equal cost ranges.  A range starts inside
+// unit u0 at step j0 and ends inside unit u1 before step j1; the CTA does the head of u1 (steps [0, j1)) FIRST and
+// publishes it, then its whole units, then the tail of u0 (steps [j0, T)) LAST, waiting for the head that the
+// previous CTA published at the very beginning of its own range -- no circular wait, and the wait is over long before
+// it is reached.  flags[u] (zeroed before the launch) = head of unit u complete.
+__device__ __forceinline__ void sweep_locate(long b, int T, long C, int* u, int* j) {
+    *u = (int)(b / C);
+    const long rem = b - (long)*u * C;
+    int jj = (int)((sqrt(4.0 * (double)rem + 1.0) - 1.0) * 0.5);
+    while ((long)jj * (jj + 1) < rem) ++jj;
+    while (jj > 0 && (long)(jj - 1) * jj >= rem) --jj;
+    if (jj >= T) { jj = 0; *u += 1; }
+    *j = jj;                                   // smallest j with j (j + 1) >= rem: steps >= j lie at or after b
+}
+
+__global__ void __launch_bounds__(NTHR, 1)
+cross_sweep_kernel(MatArgs a, double* X, long x_stride, int xT, int units, CrossArgs cr, int* flags) {
+    extern __shared__ __align__(16) double smem[];
+    const ThreadCoord tc;
+    __shared__ uint64_t bars[2 * NSTAGE];
+    Ring ring;
+    ring_init(ring, bars);
+    const int T = a.T;
+    const long C = (long)T * (T + 1), W = (long)units * C;
+    int u0, j0, u1, j1;
+    sweep_locate(W * blockIdx.x / gridDim.x, T, C, &u0, &j0);
+    sweep_locate(W * (blockIdx.x + 1) / gridDim.x, T, C, &u1, &j1);
+
+    auto steps = [&](int u, int ja, int jb) {
+        const int p = u / xT, i = u % xT;
+        const double* Ap = a.A + (long)p * a.mat_stride;
+        double* Xp = X + (long)p * x_stride;
+        const double* arows = Xp + (long)i * TB * a.lda;
+        const PairParams q = a.pp[p];
+        const double* trow = cr.trow + (long)p * cr.lrow + i * TB;
+        for (int j = ja; j < jb; ++j) {
+            const double* brows = Ap + (long)j * TB * a.lda;
+            Acc acc;
+            acc_zero(acc);
+            gemm_nt_loop<false>(acc, [&](int kt) { return SliceSrc{arows + kt * BK, a.lda, brows + kt * BK, a.lda}; },
+                                j * (TB / BK), smem, ring, tc);
+            double* S = smem;
+            double* stages = smem + TB * LDS;
+            const double* Dj = a.D + ((long)p * a.T + j) * (TB * TB);
+            __syncthreads();
+            epi_prefill_D(Dj, stages, ring, tc);
+            {
+                const double* tcol = a.ts + (long)p * a.lda + j * TB;
+                double xr[8];
+#pragma unroll
+                for (int mi = 0; mi < 8; ++mi) xr[mi] = trow[tc.row(mi)];
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) {
+                    const double2 xc = *reinterpret_cast<const double2*>(tcol + tc.col(ni, 0));
+#pragma unroll
+                    for (int mi = 0; mi < 8; ++mi) {
+                        const int r = i * TB + tc.row(mi), c = j * TB + tc.col(ni, 0);
+                        acc.v[mi][ni][0] = cross_element(cr.kind, cr.fam, q, r, c, cr.nrow, a.m, xr[mi], xc.x) - acc.v[mi][ni][0];
+                        acc.v[mi][ni][1] = cross_element(cr.kind, cr.fam, q, r, c + 1, cr.nrow, a.m, xr[mi], xc.y) - acc.v[mi][ni][1];
+                    }
+                }
+            }
+            acc_to_smem<LDS>(acc, S, tc);
+            __syncthreads();
+            Acc out;
+            acc_zero(out);
+            epi_product_SxDt(out, S, Dj, stages, ring, tc, true);
+            double* dst = Xp + (long)i * TB * a.lda + j * TB;
+#pragma unroll
+            for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni)
+                    *reinterpret_cast<double2*>(dst + (long)tc.row(mi) * a.lda + tc.col(ni, 0)) =
+                        make_double2(out.v[mi][ni][0], out.v[mi][ni][1]);
+            __syncthreads();   // X_ij is visible to the whole CTA (it is an operand of the next step); smem is free again
+        }
+    };
+
+    const bool split_tail = j0 > 0;                                  // u0's head belongs to the previous CTA
+    const bool split_head = j1 > 0 && u1 < units;                    // u1's tail belongs to the next CTA
+    if (u0 == u1) {                                                  // the whole range lies inside one unit
+        if (split_tail) {
+            if (tc.tid == 0) { while (atomicAdd(&flags[u0], 0) == 0) __nanosleep(64); __threadfence(); }
+            __syncthreads();
+        }
+        steps(u0, j0, j1);
+        return;                                                      // (a later CTA waiting on u0's head waits on OUR predecessor)
+    }
+    if (split_head) {
+        steps(u1, 0, j1);
+        __threadfence();
+        __syncthreads();
+        if (tc.tid == 0) atomicExch(&flags[u1], 1);
+    }
+    for (int u = split_tail ? u0 + 1 : u0; u < u1; ++u) steps(u, 0, T);
+    if (split_tail) {
+        if (tc.tid == 0) { while (atomicAdd(&flags[u0], 0) == 0) __nanosleep(64); __threadfence(); }
+        __syncthreads();
+        steps(u0, j0, T);
+    }
 }
 
 // ---- forward / backward substitution with the block factor ------------------------------
@@ -774,13 +911,14 @@ __global__ void __launch_bounds__(NTHR, 1) trtri_row_kernel(MatArgs a, int i, Pr
             (i - j) * (TB / BK), smem, ring, tc);
     double* G = smem;
     double* stages = smem + TB * LDS;
-    __syncthreads();   // ring memory is re-used for G
+    const double* Di = a.D + ((long)p * a.T + i) * (TB * TB);
+    __syncthreads();   // ring memory is re-used for G and the epilogue's stages
+    epi_prefill_D(Di, stages, ring, tc);   // inv(L_ii) slices fly while the accumulators go to shared memory
     acc_to_smem<LDS>(acc, G, tc);      // G[k][n]
     __syncthreads();
     Acc out;
     acc_zero(out);
-    const double* Di = a.D + ((long)p * a.T + i) * (TB * TB);
-    epi_product_DxG(out, Di, G, stages, ring, tc);
+    epi_product_DxG(out, Di, G, stages, ring, tc, true);
     // transposed store: U[j*128 + col][i*128 + row] = -out[row][col]
     double* dst = Ap + (long)j * TB * a.lda + i * TB;
 #pragma unroll

@@ -49,11 +49,57 @@ std_kernel(MatArgs a, const double* __restrict__ X, long x_stride, int nrow, dou
     }
 }
 
+// K_zz as a function of the (scaled like cr.trow) distance d between two estimation points (gpkernels.py:641).
+__device__ __forceinline__ double kzz_element(int fam, const PairParams& pr, double d) {
+    const double d2 = d * d;
+    if (fam == 0) {
+        const double ell2 = pr.ell * pr.ell;
+        const double kap = pr.sig2 * gpbo_exp_neg(-gpbo_div(d2, 2 * ell2, 0.5 * pr.inv_ell2));
+        return gpbo_div((1 - gpbo_div(d2, ell2, pr.inv_ell2)) * kap, ell2, pr.inv_ell2);
+    }
+    // Matern: -kappa''(tau), rows are t' / ell
+    const double K = fabs(d) * (fam == 3 ? 1.7320508075688772 : 2.23606797749979);
+    const double ex = gpbo_exp_neg(-K);
+    const double a2 = (fam == 3 ? 3.0 : 5.0) * pr.inv_ell2;
+    return fam == 3 ? pr.sig2 * a2 * (1.0 - K) * ex : pr.sig2 * (a2 / 3.0) * (1.0 + K - K * K) * ex;
+}
+
+// Row N2: the reference's estimation grid is np.linspace (PDEs/main.py:101-105), so K_zz is Toeplitz --
+// m' distinct values per GP instead of m'^2 exponentials.  One CTA per GP: decides whether the (unscaled) points are
+// equispaced to rounding (|t_k - t_0 - k h| <= 8 eps max|t|) and tabulates K_zz by lag from the scaled rows the Schur
+// kernel uses, tab[p][k] = K_zz(trow[k] - trow[0]).  flag[p] = 1: schur_kernel indexes the table by r - c.
+__global__ void __launch_bounds__(NTHR)
+kzz_table_kernel(const double* __restrict__ src, long src_stride, CrossArgs cr, const PairParams* __restrict__ pp,
+                 double* __restrict__ tab, int* __restrict__ flag) {
+    __shared__ double red[NTHR / 32];
+    const int p = blockIdx.x, n = cr.nrow;
+    const double* sp = src + (long)p * src_stride;
+    const double* tr = cr.trow + (long)p * cr.lrow;
+    const PairParams pr = pp[p];
+    const double s0 = sp[0], s1 = sp[n - 1];
+    const double h = n > 1 ? (s1 - s0) / (double)(n - 1) : 0.0;
+    double dev = 0.0;
+    for (int k = threadIdx.x; k < n; k += NTHR) {
+        dev = fmax(dev, fabs((sp[k] - s0) - (double)k * h));
+        tab[(long)p * cr.lrow + k] = kzz_element(cr.fam, pr, tr[k] - tr[0]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dev = fmax(dev, __shfl_xor_sync(0xffffffffu, dev, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dev;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < NTHR / 32; ++w) dev = fmax(dev, red[w]);
+        const double scale = fmax(fabs(s0), fabs(s1));
+        flag[p] = (n > 2 && h != 0.0 && dev <= 8.0 * 2.220446049250313e-16 * scale) ? 1 : 0;
+    }
+}
+
 // C = K_zz - V^T V (gpkernels.py:491-493, 641): tile (I, J), I >= J, of the Schur complement of the
 // joint covariance [[K_yy, K_zy^T], [K_zy, K_zz]]; written symmetric into the unpadded m' x m' output.
+// kzz_tab / kzz_flag (may be null): Toeplitz table of kzz_table_kernel.
 __global__ void __launch_bounds__(NTHR, 1)
 schur_kernel(MatArgs a, const double* __restrict__ X, long x_stride, CrossArgs cr, int ntiles,
-             double* __restrict__ C, long c_stride) {
+             double* __restrict__ C, long c_stride, const double* __restrict__ kzz_tab, const int* __restrict__ kzz_flag) {
     extern __shared__ __align__(16) double smem[];
     const ThreadCoord tc;
     const int p = blockIdx.x / ntiles, q = blockIdx.x % ntiles;
@@ -76,10 +122,11 @@ schur_kernel(MatArgs a, const double* __restrict__ X, long x_stride, CrossArgs c
                             a.lda / BK, smem, ring, tc);
     }
     const PairParams pr = a.pp[p];
-    const double ell2 = pr.ell * pr.ell;
     const double* tr = cr.trow + (long)p * cr.lrow;
     double* Cp = C + (long)p * c_stride;
     const int n = cr.nrow;
+    const bool toeplitz = kzz_flag != nullptr && kzz_flag[p] != 0;
+    const double* tab = kzz_tab + (long)p * cr.lrow;
     double xr[8], xc[4][2];
 #pragma unroll
     for (int mi = 0; mi < 8; ++mi) xr[mi] = tr[I * TB + tc.row(mi)];
@@ -95,18 +142,7 @@ schur_kernel(MatArgs a, const double* __restrict__ X, long x_stride, CrossArgs c
             for (int e = 0; e < 2; ++e) {
                 const int r = I * TB + tc.row(mi), c = J * TB + tc.col(ni, e);
                 if (r < n && c < n && c <= r) {
-                    const double d = xr[mi] - xc[ni][e];
-                    const double d2 = d * d;
-                    double kzz;
-                    if (cr.fam == 0) {
-                        const double kap = pr.sig2 * gpbo_exp_neg(-gpbo_div(d2, 2 * ell2, 0.5 * pr.inv_ell2));
-                        kzz = gpbo_div((1 - gpbo_div(d2, ell2, pr.inv_ell2)) * kap, ell2, pr.inv_ell2);
-                    } else {   // Matern: -kappa''(tau), rows are t' / ell
-                        const double K = fabs(d) * (cr.fam == 3 ? 1.7320508075688772 : 2.23606797749979);
-                        const double ex = gpbo_exp_neg(-K);
-                        const double a2 = (cr.fam == 3 ? 3.0 : 5.0) * pr.inv_ell2;
-                        kzz = cr.fam == 3 ? pr.sig2 * a2 * (1.0 - K) * ex : pr.sig2 * (a2 / 3.0) * (1.0 + K - K * K) * ex;
-                    }
+                    const double kzz = toeplitz ? tab[r - c] : kzz_element(cr.fam, pr, xr[mi] - xc[ni][e]);
                     const double v = kzz - acc.v[mi][ni][e];
                     Cp[(long)r * n + c] = v;
                     if (r != c) Cp[(long)c * n + r] = v;
@@ -245,6 +281,64 @@ assemble_general_kernel(const double* __restrict__ t1, long t1_stride, int n1, c
             orow[0] = va;
             if (two) orow[1] = vb;
         }
+    }
+}
+
+// Flat kernel for matrices with a short second dimension (the reference's own m' >> m shape, e.g. 3200 x 200): the
+// 32 x 512 tiles of the general kernel would leave most threads without a column, so the row-major output is
+// treated as ONE contiguous array: a CTA owns FLAT_E consecutive elements, every thread writes 16-byte pairs that
+// are 512 elements apart (fully coalesced whatever n2 is), row / column indices advance incrementally (no division
+// in the loop), and the scaled abscissae of the rows the chunk touches and of all n2 columns are staged in shared
+// memory once per CTA.
+constexpr int FLAT_E = 8192;          // elements per CTA
+constexpr int FLAT_MAX_N2 = 2048;     // columns staged in shared memory
+constexpr int FLAT_MIN_N2 = 8;        // below this a chunk would span more rows than the row buffer holds
+constexpr int FLAT_ROWS = FLAT_E / FLAT_MIN_N2 + 2;
+
+template <int FAM, int KIND>
+__global__ void __launch_bounds__(NTHR)
+assemble_flat_kernel(const double* __restrict__ t1, long t1_stride, int n1, const double* __restrict__ t2,
+                     long t2_stride, int n2, const double* __restrict__ theta, double* __restrict__ out,
+                     long out_stride) {
+    __shared__ double x1s[FLAT_ROWS];
+    __shared__ double x2s[FLAT_MAX_N2];
+    const int p = blockIdx.y;
+    const AsmConsts k(theta + 3 * p);
+    constexpr bool scaled = AsmScaled<FAM, KIND>::value;
+    constexpr bool has_diag = (KIND == 0 || KIND == 1);
+    const long total = (long)n1 * n2;
+    const long e0 = (long)blockIdx.x * FLAT_E;
+    const long e1 = e0 + FLAT_E < total ? e0 + FLAT_E : total;
+    const int r_first = (int)(e0 / n2), r_last = (int)((e1 - 1) / n2);
+    const double* a1 = t1 + (long)p * t1_stride;
+    const double* a2 = t2 + (long)p * t2_stride;
+    for (int i = threadIdx.x; i <= r_last - r_first; i += NTHR) {
+        const double v = a1[r_first + i];
+        x1s[i] = scaled ? v / k.ell : v;
+    }
+    for (int i = threadIdx.x; i < n2; i += NTHR) {
+        const double v = a2[i];
+        x2s[i] = scaled ? v / k.ell : v;
+    }
+    __syncthreads();
+    double* o = out + (long)p * out_stride;
+    const bool vec = (reinterpret_cast<uintptr_t>(o) & 15) == 0;      // e0 and the pair offsets are even
+    long e = e0 + 2 * threadIdx.x;
+    int r = (int)(e / n2), c = (int)(e - (long)r * n2);
+    const int dr = (2 * NTHR) / n2, dc = (2 * NTHR) % n2;
+    for (; e < e1; e += 2 * NTHR) {
+        const double va = assemble_element<FAM, KIND>(k, has_diag && r == c, x1s[r - r_first], x2s[c]);
+        int r2 = r, c2 = c + 1;
+        if (c2 == n2) { c2 = 0; ++r2; }
+        if (e + 1 < e1) {
+            const double vb = assemble_element<FAM, KIND>(k, has_diag && r2 == c2, x1s[r2 - r_first], x2s[c2]);
+            if (vec) *reinterpret_cast<double2*>(o + e) = make_double2(va, vb);
+            else { o[e] = va; o[e + 1] = vb; }
+        } else {
+            o[e] = va;
+        }
+        r += dr; c += dc;
+        if (c >= n2) { c -= n2; ++r; }
     }
 }
 

@@ -101,50 +101,17 @@ __device__ __forceinline__ void small_block_sum(double (&v)[NV], double* red, do
     __syncthreads();
 }
 
-// Cholesky of the 32 x 32 diagonal block at (o, o) of the packed matrix, by all NT threads (same scheme as
-// chol32_block in kernels_chol.cuh: right-looking with unscaled columns, one barrier per step, the 32 square roots
-// at the end).  dinv[o + i] = 1 / L_ii.  rsv: 32 doubles of scratch.  Returns (uniformly) whether a pivot was <= 0.
-template <int NT>
-__device__ __forceinline__ bool small_chol32(double* L, int o, double* dinv, double* rsv) {
-    constexpr int TPR = NT / SB;                  // threads per row
-    const int tid = threadIdx.x;
-    const int r = tid / TPR, cg = tid % TPR;
-    double* Lr = L + tri(o + r) + o;
-    bool bad = false;
-    for (int j = 0; j < SB - 1; ++j) {
-        double d = L[tri(o + j) + o + j];
-        if (!(d > 0.0)) { bad = true; d = 1.0; }
-        const double inv_d = __drcp_rn(d);
-        if (tid == 0) rsv[j] = d;
-        if (r > j) {
-            const double w = Lr[j] * inv_d;
-#pragma unroll
-            for (int q = 0; q < SB / TPR; ++q) {
-                const int c = cg + TPR * q;
-                if (c > j && c <= r) Lr[c] = fma(-w, L[tri(o + c) + o + j], Lr[c]);
-            }
-        }
-        __syncthreads();
-    }
-    {
-        double d = L[tri(o + SB - 1) + o + SB - 1];
-        if (!(d > 0.0)) { bad = true; d = 1.0; }
-        if (tid == 0) rsv[SB - 1] = d;
+// Cholesky of the 32 x 32 diagonal block at (o, o) of the packed matrix by warp 0 (warp_chol32, kernels_chol.cuh:
+// registers + shuffles, no barrier inside).  dinv[o + i] = 1 / L_ii.  flag: one double of scratch.  Ends with
+// __syncthreads(); returns (uniformly) whether a pivot was <= 0.  flag: 33 doubles of scratch.
+__device__ __forceinline__ bool small_chol32(double* L, int o, double* dinv, double* flag) {
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        const bool bad = warp_chol32(L + tri(o + lane) + o, dinv + o + lane);
+        if (lane == 0) *flag = bad ? 1.0 : 0.0;
     }
     __syncthreads();
-    if (tid < SB) rsv[tid] = rsqrt(rsv[tid]);
-    __syncthreads();
-#pragma unroll
-    for (int q = 0; q < SB / TPR; ++q) {
-        const int c = cg + TPR * q;
-        if (c <= r) {
-            const double v = Lr[c];
-            Lr[c] = (c == r && !(v > 0.0)) ? 1.0 : v * rsv[c];
-        }
-    }
-    if (tid < SB) dinv[o + tid] = rsv[tid];
-    __syncthreads();
-    return bad;
+    return *flag != 0.0;
 }
 
 // One LML + gradient evaluation by the whole CTA.  sm: dynamic shared memory (small_smem_bytes(n)).
@@ -199,7 +166,7 @@ __device__ void small_eval(const SmallProblem& pr, int gp, double th0, double th
     bool bad = false;
     for (int kb = 0; kb < nblk; ++kb) {
         const int o = kb * SB;
-        bad |= small_chol32<NT>(L, o, dinv, red);
+        bad |= small_chol32(L, o, dinv, red);
         small_mark(clk, 1);
         const int R0 = o + SB, nb = n - R0;
         if (nb <= 0) break;
@@ -449,7 +416,7 @@ __device__ void small_eval(const SmallProblem& pr, int gp, double th0, double th
 
 // Fixed-theta entry: one CTA per pair.
 template <int NT, int FAM>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, NT == 64 ? 6 : 1)
 small_lml_grad_kernel(SmallProblem pr, const double* __restrict__ theta, const int* __restrict__ gp_of, int B,
                       double* __restrict__ lml, double* __restrict__ grad, int* __restrict__ status) {
     extern __shared__ __align__(16) double sm[];
@@ -469,7 +436,7 @@ small_lml_grad_kernel(SmallProblem pr, const double* __restrict__ theta, const i
 
 // The whole multi-start fit: persistent CTAs pull pairs from `counter` and run each pair's L-BFGS-B to termination.
 template <int NT, int FAM>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, NT == 64 ? 6 : 1)
 small_fit_kernel(SmallProblem pr, const double* __restrict__ starts, const int* __restrict__ gp_of, int B, SmallBox box,
                  LbOptions o, int* __restrict__ counter, double* __restrict__ theta_opt, double* __restrict__ fun,
                  int* __restrict__ nfev, int* __restrict__ nit, int* __restrict__ opt_status) {

@@ -68,8 +68,9 @@ __device__ __forceinline__ void ring_init(Ring& r, uint64_t* bars) {
 
 // Runs nk slices through the ring.  stage(st, kt): issue this thread's cp.async for slice kt into stage st.
 // compute(st, kt, half): the DMMA work of slice kt (half = integral_constant 0 / 1: first / second BK/8 k-steps).
+// `prefilled`: the first NSTAGE - 1 slices were already issued by ring_prefill (same nk, same stage functor).
 template <class STAGE, class COMPUTE>
-__device__ __forceinline__ void ring_pipeline(Ring& ring, int nk, STAGE stage, COMPUTE compute) {
+__device__ __forceinline__ void ring_pipeline(Ring& ring, int nk, STAGE stage, COMPUTE compute, bool prefilled = false) {
     if (nk <= 0) return;
     const int lane = threadIdx.x & 31;
     const int base = ring.count;
@@ -80,9 +81,11 @@ __device__ __forceinline__ void ring_pipeline(Ring& ring, int nk, STAGE stage, C
         stage(st, kt);
         mbar_cp_arrive(&ring.full[st]);
     };
+    if (!prefilled) {
 #pragma unroll
-    for (int s = 0; s < NSTAGE - 1; ++s)
-        if (s < nk) push(s);
+        for (int s = 0; s < NSTAGE - 1; ++s)
+            if (s < nk) push(s);
+    }
     for (int kt = 0; kt < nk; ++kt) {
         const int gi = base + kt;
         const int cs = gi % NSTAGE;
@@ -95,6 +98,23 @@ __device__ __forceinline__ void ring_pipeline(Ring& ring, int nk, STAGE stage, C
         if (lane == 0) mbar_arrive(&ring.empty[cs]);
     }
     ring.count = base + nk;
+}
+
+// Issue the first NSTAGE - 1 slices of a pipeline ahead of time (e.g. before an epilogue's register math), so that
+// their global -> shared latency is hidden; the matching ring_pipeline call passes prefilled = true.
+// Every warp must have finished reading the ring memory the stages are written to (__syncthreads() before).
+template <class STAGE>
+__device__ __forceinline__ void ring_prefill(Ring& ring, int nk, STAGE stage) {
+    const int base = ring.count;
+#pragma unroll
+    for (int s = 0; s < NSTAGE - 1; ++s)
+        if (s < nk) {
+            const int gi = base + s;
+            const int st = gi % NSTAGE;
+            if (gi >= NSTAGE) mbar_wait(&ring.empty[st], ((gi / NSTAGE) - 1) & 1);
+            stage(st, s);
+            mbar_cp_arrive(&ring.full[st]);
+        }
 }
 
 // Stage one 128 x 16 operand slice (rows `ld` apart in global memory) into padded shared rows.
@@ -254,8 +274,15 @@ __device__ __forceinline__ void acc_to_smem(const Acc& acc, double* S, const Thr
 // out += S * Dm^T : S is a shared 128x128 tile [r][k] (stride LDS), complete and visible to the CTA;
 // Dm is a LOWER-TRIANGULAR 128x128 global block (a block inverse D, row stride 128) whose rows [n][k] are streamed
 // through `stages`; column groups that lie entirely above the diagonal of Dm are skipped.
+// The slices of a 128 x 128 block inverse Dm for the epilogue products below, issued early.
+__device__ __forceinline__ void epi_prefill_D(const double* __restrict__ Dm, double* stages, Ring& ring,
+                                              const ThreadCoord& tc) {
+    ring_prefill(ring, TB / BK, [&](int st, int kt) { stage_slice(stages + st * STAGE_DBL, Dm + kt * BK, TB, tc.tid); });
+}
+
 __device__ __forceinline__ void epi_product_SxDt(Acc& out, const double* S, const double* __restrict__ Dm,
-                                                 double* stages, Ring& ring, const ThreadCoord& tc) {
+                                                 double* stages, Ring& ring, const ThreadCoord& tc,
+                                                 bool prefilled = false) {
     const double* sa0 = S + (tc.wm * 8 + tc.g) * LDS + tc.c;
     const int ob = (tc.wn * 8 + tc.g) * LDT + tc.c;
     ring_pipeline(
@@ -263,13 +290,15 @@ __device__ __forceinline__ void epi_product_SxDt(Acc& out, const double* S, cons
         [&](int st, int kt, auto half) {
             mma_half_tri_dispatch<LDS, LDT, decltype(half)::value, SKIP_B_LO>(out, sa0 + kt * BK,
                                                                               stages + st * STAGE_DBL + ob, kt);
-        });
+        },
+        prefilled);
 }
 
 // out += Dm * G : Dm is a LOWER-TRIANGULAR 128x128 global block [r][k] (a block inverse D) streamed through
 // `stages`; G is a shared 128x128 tile stored [k][n] (stride LDS), complete and visible to the CTA.
 __device__ __forceinline__ void epi_product_DxG(Acc& out, const double* __restrict__ Dm, const double* G,
-                                                double* stages, Ring& ring, const ThreadCoord& tc) {
+                                                double* stages, Ring& ring, const ThreadCoord& tc,
+                                                bool prefilled = false) {
     const int oa = (tc.wm * 8 + tc.g) * LDT + tc.c;
     ring_pipeline(
         ring, TB / BK, [&](int st, int kt) { stage_slice(stages + st * STAGE_DBL, Dm + kt * BK, TB, tc.tid); },
@@ -303,7 +332,8 @@ __device__ __forceinline__ void epi_product_DxG(Acc& out, const double* __restri
                 case 6: body(std::integral_constant<int, 6>{}); break;
                 default: body(std::integral_constant<int, 7>{}); break;
             }
-        });
+        },
+        prefilled);
 }
 
 }  // namespace gpbo

@@ -191,9 +191,10 @@ int gpbo_weighted_products_host(gpbo_ctx* ctx, const double* sqrtw, int G, int n
 
 /* Per-kernel-class device timing (CUDA events on the launching stream), for bench.py's roofline.
  * Classes: 0 prep 1 chol_diag 2 chol_panel 3 trsv 4 trtri 5 lauum_grad 6 finalize 7 cross_panel
- *          8 schur 9 mean_std 10 assemble 11 sqrtw 12 small (in-shared path).  `ms` and `launches` are arrays of
+ *          8 schur 9 mean_std (fused kernel-row x alpha means) 10 assemble 11 sqrtw 12 small (in-shared path)
+ *          13 std (row norms of V for the predictive std).  `ms` and `launches` are arrays of
  * GPBO_NCLASS entries, accumulated since the last gpbo_profile_enable(ctx, 1). */
-#define GPBO_NCLASS 13
+#define GPBO_NCLASS 14
 int gpbo_profile_enable(gpbo_ctx* ctx, int on);
 int gpbo_profile_get(gpbo_ctx* ctx, double* ms, long long* launches);
 

@@ -394,9 +394,16 @@ def test_moments_many_estimation_points(ctx):
         assert rel(state[gi], ref["state_estimate"]) <= 1e-9
         assert rel(ddt[gi], ref["ddt_estimate"]) <= 1e-9
         assert rel(cov[gi], ref["ddt_covariance"]) <= 1e-8
+    # sqrtW through its defining identity, against the same residual of the reference's eigh route (cond ~ 1e11:
+    # both are limited by cond * eps, gpkernels.py:496-504)
     x = np.random.default_rng(0).standard_normal(3200)
     A = cov[0] + 1e-8 * np.eye(3200)
-    assert np.abs(w[0] @ (A @ (w[0] @ x)) - x).max() <= 1e-4 * np.abs(x).max()
+    ours = np.abs(w[0] @ (A @ (w[0] @ x)) - x).max() / np.abs(x).max()
+    wref, _ = _eigh_sqrtw(cov[0], 1e-8)
+    theirs = np.abs(wref @ (A @ (wref @ x)) - x).max() / np.abs(x).max()
+    record("sqrtw_identity_residual[m'=3200] newton-schulz", ours)
+    record("sqrtw_identity_residual[m'=3200] eigh", theirs)
+    assert ours <= max(1e-4, 3 * theirs), (ours, theirs)
 
 
 # ------------------------------------------------------------------ optimiser

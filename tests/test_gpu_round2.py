@@ -241,3 +241,59 @@ def test_sqrtw_scaled_iteration_count(ctx, name):
         res = np.abs(W[k] @ A @ W[k] - np.eye(n)).max()
         record("sqrtw_identity_residual[real configs]", res)
         assert res <= 1e-4
+
+
+# ------------------------------------------------------------------ row N2: Toeplitz K_zz, prediction sweep
+@pytest.mark.parametrize("grid", ["linspace", "jittered", "offset_linspace", "per_gp"])
+def test_ddt_covariance_toeplitz_and_general_paths(ctx, grid):
+    """``K_zz`` (gpkernels.py:641) comes from a per-GP table by lag when the estimation points are equispaced (the
+    reference's np.linspace grid, PDEs/main.py:101-105) and from the element formula otherwise; both against the
+    oracle, 1e-10 of the covariance scale.  m' = 700 spans six 128-tiles; 'offset' puts the grid far from 0 (the lag
+    substitution t_i - t_j -> t_{i-j} - t_0 is then accurate to fewer digits of d)."""
+    if ctx.path != "blocked":
+        pytest.skip("prediction path is shared by both fixtures")
+    t, y = orc.synthetic_trajectories(2, 300, seed=5)
+    th = np.log(np.array([[2.5, 0.05, 1e-2], [0.7, 0.3, 3e-3]]))
+    n = 700
+    rng = np.random.default_rng(11)
+    shift = 0.0
+    if grid == "linspace":
+        t_est = np.linspace(0, 1, n)
+    elif grid == "jittered":
+        t_est = np.sort(np.linspace(0, 1, n) + 1e-4 * rng.standard_normal(n))
+    elif grid == "offset_linspace":
+        shift = 1000.0
+        t_est = np.linspace(shift, shift + 1, n)
+    else:
+        t_est = np.stack([np.linspace(0, 1, n), np.sort(rng.uniform(0, 1, n))])      # GP 0 Toeplitz, GP 1 general
+    T = np.tile(t + shift, (2, 1))
+    state, ddt, cov, st = ctx.lstsq_moments(T, y, th, t_est)
+    assert np.all(st == 0)
+    for gi in range(2):
+        te = t_est if t_est.ndim == 1 else t_est[gi]
+        ref = orc.np_lstsq_moments(t + shift, y[gi], th[gi], te, want_sqrtW=False)
+        err = rel(cov[gi], ref["ddt_covariance"])
+        record(f"ddt_cov_rel[toeplitz test, {grid}]", err)
+        assert err <= (1e-10 if shift == 0.0 else 1e-9)
+        assert rel(state[gi], ref["state_estimate"]) <= 1e-10 and rel(ddt[gi], ref["ddt_estimate"]) <= 1e-10
+        assert np.array_equal(cov[gi], cov[gi].T)
+
+
+def test_prediction_sweep_many_row_tiles(ctx):
+    """The persistent row-sweep TRSM (one launch, sweeps cut into equal cost ranges across CTAs; taken when the row
+    tiles fill the GPU): 3 GPs x m' = 6500 -> 153 row tiles, against the per-column launches on a subset of GPs (one
+    GP -> 51 tiles -> per-column path) and against the oracle."""
+    if ctx.path != "blocked":
+        pytest.skip("prediction path is shared by both fixtures")
+    t, y = orc.synthetic_trajectories(3, 520, seed=8)
+    th = np.log(np.array([[2.5, 0.05, 1e-2], [0.7, 0.3, 3e-3], [1.3, 0.1, 1e-3]]))
+    t_est = np.linspace(-0.05, 1.05, 6500)
+    T = np.tile(t, (3, 1))
+    mean, std, _ = ctx.predict(T, y, th, t_est)[:3]
+    for gi in range(3):
+        m1, s1 = ctx.predict(T[gi:gi + 1], y[gi:gi + 1], th[gi:gi + 1], t_est)[:2]
+        assert rel(mean[gi], m1[0]) <= 1e-13
+        assert rel(std[gi], s1[0], scale=np.abs(s1[0]).max()) <= 1e-9
+        m0, s0 = orc.np_predict(t, y[gi], th[gi], t_est)
+        assert rel(mean[gi], m0) <= 1e-10
+        assert rel(std[gi], s0) <= 1e-7
