@@ -13,7 +13,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgpbo.so")
+# GPBO_LIB: an alternative build of the same library (A/B measurements of kernel variants, tools/ab/); never a fallback
+LIB_PATH = os.environ.get("GPBO_LIB") or os.path.join(_HERE, "libgpbo.so")
 
 NCLASS = 14
 KERNEL_CLASSES = ("prep", "chol_diag", "chol_panel", "trsv", "trtri", "lauum_grad", "finalize",

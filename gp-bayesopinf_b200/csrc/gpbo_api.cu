@@ -87,6 +87,12 @@ struct gpbo_ctx {
     DevBuf wp_lhs, wp_rhs, wp_olhs, wp_orhs;
     // split-K partial tiles (small batches)
     DevBuf pre;
+    // TMA tensor maps of the wave buffers (A, D, DT), re-encoded when a buffer moves or the padded size changes
+    TmaMaps tmaps;
+    const void* tm_A = nullptr; const void* tm_D = nullptr; const void* tm_DT = nullptr;
+    size_t tm_bytes_A = 0, tm_bytes_D = 0;
+    int tm_mpad = 0;
+    bool tma_ok = false;
     // pinned staging for the optimiser rounds
     double* h_theta = nullptr; double* h_lml = nullptr; double* h_grad = nullptr; int* h_gpof = nullptr;
     size_t h_cap = 0;
@@ -239,27 +245,70 @@ MatArgs mat_args(gpbo_ctx* c, int m, int m_pad) {
     return a;
 }
 
+// ---- TMA tensor maps ------------------------------------------------------------------------------------------
+// cuTensorMapEncodeTiled is a driver-API entry point; it is fetched through the runtime (no -lcuda at link time).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// 2-D map over `rows` rows of `cols` doubles (row-major, contiguous), box = one operand slice (16 x 128), 128-byte swizzle.
+bool encode_slice_map(CUtensorMap* map, void* base, size_t rows, size_t cols) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn || rows == 0 || rows > 0xffffffffull) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)cols * 8};
+    const cuuint32_t box[2] = {BK, TB};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// (Re-)encode the maps of the wave buffers.  GPBO_NO_TMA=1 keeps the LDGSTS staging everywhere (A/B measurements).
+void update_tma_maps(gpbo_ctx* c, int m_pad) {
+    static const bool disabled = std::getenv("GPBO_NO_TMA") != nullptr;
+    if (disabled) { c->tma_ok = false; return; }
+    if (c->tma_ok && c->tm_A == c->A.p && c->tm_D == c->D.p && c->tm_DT == c->DT.p && c->tm_mpad == m_pad &&
+        c->tm_bytes_A == c->A.bytes && c->tm_bytes_D == c->D.bytes)
+        return;
+    const size_t rows_a = c->A.bytes / ((size_t)m_pad * 8), rows_d = std::min(c->D.bytes, c->DT.bytes) / ((size_t)TB * 8);
+    c->tma_ok = encode_slice_map(&c->tmaps.A, c->A.p, rows_a, (size_t)m_pad) &&
+                encode_slice_map(&c->tmaps.D, c->D.p, rows_d, TB) && encode_slice_map(&c->tmaps.DT, c->DT.p, rows_d, TB);
+    c->tm_A = c->A.p; c->tm_D = c->D.p; c->tm_DT = c->DT.p; c->tm_mpad = m_pad;
+    c->tm_bytes_A = c->A.bytes; c->tm_bytes_D = c->D.bytes;
+}
+
 // cudaFuncSetAttribute is per device: remember which devices have been configured
 bool g_attr_done[64] = {false};
 int set_kernel_attrs() {
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     if (dev >= 0 && dev < 64 && g_attr_done[dev]) return GPBO_OK;
-    CUDA_TRY(cudaFuncSetAttribute(chol_diag_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
-    CUDA_TRY(cudaFuncSetAttribute(chol_diag_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
-    CUDA_TRY(cudaFuncSetAttribute(chol_diag_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
-    CUDA_TRY(cudaFuncSetAttribute(chol_diag_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
-    CUDA_TRY(cudaFuncSetAttribute(chol_panel_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
-    CUDA_TRY(cudaFuncSetAttribute(chol_panel_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
-    CUDA_TRY(cudaFuncSetAttribute(lauum_grad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
-    CUDA_TRY(cudaFuncSetAttribute(lauum_grad_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
-    CUDA_TRY(cudaFuncSetAttribute(chol_panel_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
-    CUDA_TRY(cudaFuncSetAttribute(chol_panel_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
-    CUDA_TRY(cudaFuncSetAttribute(chol_panel_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
-    CUDA_TRY(cudaFuncSetAttribute(trtri_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
-    CUDA_TRY(cudaFuncSetAttribute(cross_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
-    CUDA_TRY(cudaFuncSetAttribute(splitk_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
-    CUDA_TRY(cudaFuncSetAttribute(lauum_grad_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
+#define GPBO_ATTR(K, BYTES) CUDA_TRY(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES));
+#define GPBO_ATTR_ORDER(O)                                                                                          \
+    GPBO_ATTR((chol_diag_kernel<O, false>), MAIN_SMEM) GPBO_ATTR((chol_diag_kernel<O, true>), MAIN_SMEM)              \
+    GPBO_ATTR((chol_panel_kernel<O, false, false>), TILE_SMEM) GPBO_ATTR((chol_panel_kernel<O, false, true>), TILE_SMEM)
+    GPBO_ATTR_ORDER(0) GPBO_ATTR_ORDER(1) GPBO_ATTR_ORDER(2) GPBO_ATTR_ORDER(3)
+    GPBO_ATTR((chol_panel_kernel<0, true, false>), TILE_SMEM)
+    GPBO_ATTR(trtri_row_kernel<false>, TILE_SMEM) GPBO_ATTR(trtri_row_kernel<true>, TILE_SMEM)
+    GPBO_ATTR(cross_sweep_kernel, TILE_SMEM)
+    GPBO_ATTR(splitk_partial_kernel, MAIN_SMEM)
+    GPBO_ATTR((lauum_grad_kernel<0, false>), MAIN_SMEM) GPBO_ATTR((lauum_grad_kernel<0, true>), MAIN_SMEM)
+    GPBO_ATTR((lauum_grad_kernel<3, false>), MAIN_SMEM) GPBO_ATTR((lauum_grad_kernel<3, true>), MAIN_SMEM)
+    GPBO_ATTR((lauum_grad_kernel<5, false>), MAIN_SMEM) GPBO_ATTR((lauum_grad_kernel<5, true>), MAIN_SMEM)
+#undef GPBO_ATTR_ORDER
+#undef GPBO_ATTR
     CUDA_TRY(cudaFuncSetAttribute(schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(ns_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
 #define GPBO_SYM_ATTR(F, K) CUDA_TRY(cudaFuncSetAttribute(assemble_sym_kernel<F, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, SYM_SMEM));
@@ -327,19 +376,23 @@ int factor_wave(gpbo_ctx* c, cudaStream_t s, const MatArgs& a, const double* t_d
         PreAcc pre;
         int rc = plan_split(c, s, a, 0, j, nb, a.T - j, j * (TB / BK), nullptr, 0, &pre);
         if (rc) return rc;
+        const bool tma = c->tma_ok;
+        const TmaMaps& tm = c->tmaps;
         launch(c, C_DIAG, s, [&] {
-            if (gen == 0) chol_diag_kernel<0><<<nb, NTHR, MAIN_SMEM, s>>>(a, j, pre);
-            else if (gen == 1) chol_diag_kernel<1><<<nb, NTHR, MAIN_SMEM, s>>>(a, j, pre);
-            else if (gen == 2) chol_diag_kernel<2><<<nb, NTHR, MAIN_SMEM, s>>>(a, j, pre);
-            else chol_diag_kernel<3><<<nb, NTHR, MAIN_SMEM, s>>>(a, j, pre);
+#define GPBO_DIAG(O)                                                                          \
+    if (tma) chol_diag_kernel<O, true><<<nb, NTHR, MAIN_SMEM, s>>>(a, j, pre, tm);            \
+    else chol_diag_kernel<O, false><<<nb, NTHR, MAIN_SMEM, s>>>(a, j, pre, tm)
+            if (gen == 0) { GPBO_DIAG(0); } else if (gen == 1) { GPBO_DIAG(1); } else if (gen == 2) { GPBO_DIAG(2); } else { GPBO_DIAG(3); }
+#undef GPBO_DIAG
         });
         if (j < a.T - 1) {
             const int grid = nb * (a.T - 1 - j);
             launch(c, C_PANEL, s, [&] {
-                if (gen == 0) chol_panel_kernel<0, false><<<grid, NTHR, TILE_SMEM, s>>>(a, j, nullptr, 0, 0, none, pre);
-                else if (gen == 1) chol_panel_kernel<1, false><<<grid, NTHR, TILE_SMEM, s>>>(a, j, nullptr, 0, 0, none, pre);
-                else if (gen == 2) chol_panel_kernel<2, false><<<grid, NTHR, TILE_SMEM, s>>>(a, j, nullptr, 0, 0, none, pre);
-                else chol_panel_kernel<3, false><<<grid, NTHR, TILE_SMEM, s>>>(a, j, nullptr, 0, 0, none, pre);
+#define GPBO_PANEL(O)                                                                                                   \
+    if (tma) chol_panel_kernel<O, false, true><<<grid, NTHR, TILE_SMEM, s>>>(a, j, nullptr, 0, 0, none, pre, tm);       \
+    else chol_panel_kernel<O, false, false><<<grid, NTHR, TILE_SMEM, s>>>(a, j, nullptr, 0, 0, none, pre, tm)
+                if (gen == 0) { GPBO_PANEL(0); } else if (gen == 1) { GPBO_PANEL(1); } else if (gen == 2) { GPBO_PANEL(2); } else { GPBO_PANEL(3); }
+#undef GPBO_PANEL
             });
         }
     }
@@ -355,6 +408,7 @@ int eval_wave(gpbo_ctx* c, cudaStream_t s, const double* t_dev, const double* yp
               const double* theta_dev, const int* gpof_dev, int nb, bool with_grad, double* lml, double* grad,
               int* status) {
     MatArgs a = mat_args(c, m, m_pad);
+    update_tma_maps(c, m_pad);
     int rc = factor_wave(c, s, a, t_dev, ypad, theta_dev, gpof_dev, nb, 0, !with_grad);
     if (rc) return rc;
     const int ntiles = a.T * (a.T + 1) / 2;
@@ -363,19 +417,23 @@ int eval_wave(gpbo_ctx* c, cudaStream_t s, const double* t_dev, const double* yp
             PreAcc pre;
             rc = plan_split(c, s, a, 1, i, nb, i, i * (TB / BK), nullptr, 0, &pre);
             if (rc) return rc;
-            launch(c, C_TRTRI, s, [&] { trtri_row_kernel<<<nb * i, NTHR, TILE_SMEM, s>>>(a, i, pre); });
+            launch(c, C_TRTRI, s, [&] {
+                if (c->tma_ok) trtri_row_kernel<true><<<nb * i, NTHR, TILE_SMEM, s>>>(a, i, pre, c->tmaps);
+                else trtri_row_kernel<false><<<nb * i, NTHR, TILE_SMEM, s>>>(a, i, pre, c->tmaps);
+            });
         }
         launch(c, C_TRSV, s, [&] { z_from_inverse_kernel<<<nb * a.T, NTHR, 0, s>>>(a, ypad, c->z.as<double>()); });
         launch(c, C_TRSV, s, [&] {
             alpha_from_inverse_kernel<<<nb * a.T, NTHR, 0, s>>>(a, c->z.as<double>(), c->alpha.as<double>());
         });
         launch(c, C_LAUUM, s, [&] {
-            if (c->family == 0)
-                lauum_grad_kernel<0><<<nb * ntiles, NTHR, MAIN_SMEM, s>>>(a, c->alpha.as<double>(), c->part.as<double>(), ntiles);
-            else if (c->family == 3)
-                lauum_grad_kernel<3><<<nb * ntiles, NTHR, MAIN_SMEM, s>>>(a, c->alpha.as<double>(), c->part.as<double>(), ntiles);
-            else
-                lauum_grad_kernel<5><<<nb * ntiles, NTHR, MAIN_SMEM, s>>>(a, c->alpha.as<double>(), c->part.as<double>(), ntiles);
+#define GPBO_LAUUM(F)                                                                                                            \
+    if (c->tma_ok)                                                                                                               \
+        lauum_grad_kernel<F, true><<<nb * ntiles, NTHR, MAIN_SMEM, s>>>(a, c->alpha.as<double>(), c->part.as<double>(), ntiles, c->tmaps); \
+    else                                                                                                                         \
+        lauum_grad_kernel<F, false><<<nb * ntiles, NTHR, MAIN_SMEM, s>>>(a, c->alpha.as<double>(), c->part.as<double>(), ntiles, c->tmaps)
+            if (c->family == 0) { GPBO_LAUUM(0); } else if (c->family == 3) { GPBO_LAUUM(3); } else { GPBO_LAUUM(5); }
+#undef GPBO_LAUUM
         });
     }
     launch(c, C_FINAL, s, [&] {
@@ -1208,6 +1266,7 @@ static int moments_device(gpbo_ctx* c, cudaStream_t s, int mode, const double* t
     if (rc) return rc;
     const int order = (mode == 0 || c->family != 0) ? 0 : 1;
     MatArgs a = mat_args(c, m, m_pad);
+    update_tma_maps(c, m_pad);
     for (int w0 = 0; w0 < G; w0 += cap) {
         const int nb = std::min(cap, G - w0);
         rc = factor_wave(c, s, a, t, c->ypad.as<double>(), theta + 3 * (size_t)w0, c->gpof_dev.as<int>() + w0, nb, order);
@@ -1249,7 +1308,7 @@ static int moments_device(gpbo_ctx* c, cudaStream_t s, int mode, const double* t
                     rc = plan_split(c, s, a, 2, j, nb, xT, j * (TB / BK), c->X.as<double>(), xs, &pre);
                     if (rc) return rc;
                     launch(c, C_CROSS, s, [&] {
-                        chol_panel_kernel<0, true><<<nb * xT, NTHR, TILE_SMEM, s>>>(a, j, c->X.as<double>(), xs, xT, crx, pre);
+                        chol_panel_kernel<0, true, false><<<nb * xT, NTHR, TILE_SMEM, s>>>(a, j, c->X.as<double>(), xs, xT, crx, pre, c->tmaps);
                     });
                 }
             }

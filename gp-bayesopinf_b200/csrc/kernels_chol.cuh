@@ -160,7 +160,12 @@ __device__ __forceinline__ double fast_rcp(double d) {
 // rowp: this lane's row (first of the block's 32 columns); dinv_lane receives 1 / L_rr.  Returns (warp-uniformly)
 // whether a pivot was <= 0 (the pivot is then replaced by 1).  Not inlined: its 32-double register row must not
 // inflate the register allocation of the DMMA kernels that call it.
-__device__ __noinline__ bool warp_chol32(double* rowp, double* dinv_lane) {
+#ifndef GPBO_CHOL32_INLINE
+#define GPBO_CHOL32_ATTR __noinline__
+#else
+#define GPBO_CHOL32_ATTR __forceinline__
+#endif
+__device__ GPBO_CHOL32_ATTR bool warp_chol32(double* rowp, double* dinv_lane) {
     __shared__ __align__(16) double colbuf[2][32];
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -205,6 +210,7 @@ __device__ __noinline__ bool warp_chol32(double* rowp, double* dinv_lane) {
     return bad;
 }
 
+#ifndef GPBO_CHOL32_ALLTHREADS
 // Cholesky of the 32x32 block at P[o..o+32)^2 (lower part, in place, row stride LDP) by warp 0; dinv[o+i] = 1 / L_ii.
 // `flag` = one double of scratch.  Ends with __syncthreads(); returns (uniformly) whether a pivot was <= 0.
 __device__ __forceinline__ bool chol32_block(double* P, int o, double* dinv, double* flag) {
@@ -216,6 +222,50 @@ __device__ __forceinline__ bool chol32_block(double* P, int o, double* dinv, dou
     __syncthreads();
     return *flag != 0.0;
 }
+
+#else
+// Variant kept for A/B measurements (-DGPBO_CHOL32_ALLTHREADS): all 256 threads, one CTA barrier per pivot step.
+__device__ __forceinline__ bool chol32_block(double* P, int o, double* dinv, double* rsv) {
+    const int tid = threadIdx.x;
+    const int r = tid >> 3, c8 = tid & 7;                 // row of the block, column class
+    double* Pr = P + (o + r) * LDP + o;
+    bool bad = false;
+    for (int j = 0; j < PB - 1; ++j) {
+        double d = P[(o + j) * LDP + o + j];
+        if (!(d > 0.0)) { bad = true; d = 1.0; }
+        const double inv_d = __drcp_rn(d);
+        if (tid == 0) rsv[j] = d;
+        if (r > j) {
+            const double w = Pr[j] * inv_d;
+#pragma unroll
+            for (int q = 0; q < PB / 8; ++q) {
+                const int c = c8 + 8 * q;
+                if (c > j && c <= r) Pr[c] = fma(-w, P[(o + c) * LDP + o + j], Pr[c]);
+            }
+        }
+        __syncthreads();
+    }
+    {
+        double d = P[(o + PB - 1) * LDP + o + PB - 1];
+        if (!(d > 0.0)) { bad = true; d = 1.0; }
+        if (tid == 0) rsv[PB - 1] = d;
+    }
+    __syncthreads();
+    if (tid < PB) rsv[tid] = rsqrt(rsv[tid]);
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < PB / 8; ++q) {
+        const int c = c8 + 8 * q;
+        if (c <= r) {
+            const double v = Pr[c];
+            Pr[c] = (c == r && !(v > 0.0)) ? 1.0 : v * rsv[c];
+        }
+    }
+    if (tid < PB) dinv[o + tid] = rsv[tid];
+    __syncthreads();
+    return bad;
+}
+#endif
 
 // nv = number of valid (non-padding) rows of the block: rows >= nv are identity rows (the reference's sizes
 // m = 10 ... 200 leave most of a 128-tile as padding), so only the first ceil(nv / 32) panels are factored and
@@ -296,6 +346,7 @@ __device__ __forceinline__ bool potf2_trtri_smem(double* P, double* scratch, dou
         }
         __syncthreads();
     }
+#ifndef GPBO_DIAGINV_TWOLANE
     // inverses of the 32x32 diagonal blocks, all at once: one warp per block, lane = column jc with the column in
     // registers (forward substitution over the rows, L_bb read as broadcasts); W is written transposed into the strict
     // upper part of P, where the column under construction is contiguous.
@@ -320,6 +371,31 @@ __device__ __forceinline__ bool potf2_trtri_smem(double* P, double* scratch, dou
         for (int rr = 1; rr < PB; ++rr)
             if (rr > jc) Wc[rr] = w[rr];
     }
+#else
+    // Variant kept for A/B measurements (-DGPBO_DIAGINV_TWOLANE): 64 threads per block, 2 lanes per column.
+    if ((tid >> 6) < nvb) {
+        const int o = (tid >> 6) * PB, jc = (tid & 63) >> 1, h = tid & 1;
+        double* Wc = P + (o + jc) * LDP + o;
+        const double wjj = dinv[o + jc];
+        for (int rr = 1; rr < PB; ++rr) {
+            double s0 = 0.0, s1 = 0.0;
+            if (rr > jc) {
+                const double* Lr = P + (o + rr) * LDP + o;
+                if (h == 0) s0 = Lr[jc] * wjj;
+                int k = jc + 1 + h;
+                for (; k + 2 < rr; k += 4) {
+                    s0 = fma(Lr[k], Wc[k], s0);
+                    s1 = fma(Lr[k + 2], Wc[k + 2], s1);
+                }
+                if (k < rr) s0 = fma(Lr[k], Wc[k], s0);
+            }
+            double sacc = s0 + s1;
+            sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+            if (h == 0 && rr > jc) Wc[rr] = -sacc * dinv[o + rr];
+            __syncwarp();
+        }
+    }
+#endif
     __syncthreads();
     // off-diagonal blocks of W = inv(L), block row bi; W stored transposed in the strict upper part of P
     double* Gs = scratch;
@@ -444,20 +520,25 @@ splitk_partial_kernel(MatArgs a, int mode, int idx, int ntile, int nsplit, int c
 
 // ---- Cholesky, diagonal tile of block column j ---------------------------------------------
 // S_jj = K_jj - sum_{k<j} L_jk L_jk^T (DMMA);  L_jj = chol(S_jj);  D_j = inv(L_jj).
-template <int ORDER>
-__global__ void __launch_bounds__(NTHR, 1) chol_diag_kernel(MatArgs a, int j, PreAcc pre) {
-    extern __shared__ __align__(16) double smem[];
+// TMA: the k-loop's operand slices come by cp.async.bulk.tensor through `tm` (gemm_nt_loop_tma) instead of LDGSTS.
+template <int ORDER, bool TMA>
+__global__ void __launch_bounds__(NTHR, 1)
+chol_diag_kernel(MatArgs a, int j, PreAcc pre, const __grid_constant__ TmaMaps tm) {
+    extern __shared__ __align__(1024) double smem[];
     const ThreadCoord tc;
     const int p = blockIdx.x;
     double* Ap = a.A + (long)p * a.mat_stride;
     const double* rows = Ap + (long)j * TB * a.lda;
     __shared__ uint64_t bars[2 * NSTAGE];
     Ring ring;
-    ring_init(ring, bars);
+    if (TMA) ring_init_tma(ring, bars); else ring_init(ring, bars);
     Acc acc;
     acc_zero(acc);
     if (pre.buf)
         preacc_load(acc, pre, (long)p * (a.T - j), j * (TB / BK), tc.tid);
+    else if (TMA)
+        gemm_nt_loop_tma<true>(acc, [&](int kt) { return TmaSlice{&tm.A, kt * BK, p * a.lda + j * TB, nullptr, 0, 0}; },
+                               j * (TB / BK), smem, ring, tc);
     else
         gemm_nt_loop<true>(acc, [&](int kt) { return SliceSrc{rows + kt * BK, a.lda, nullptr, 0}; }, j * (TB / BK),
                            smem, ring, tc);
@@ -541,10 +622,12 @@ __device__ __forceinline__ double cross_element(int kind, int fam, const PairPar
 // CROSS == true : X = V^T (rows = prediction points), S = cross-covariance tile; this is the
 //                 TRSM  V = L^-1 K_zy^T  of gpkernels.py:491 / _gpr.py:460 done as a continuation
 //                 of the Cholesky of the joint covariance.
-template <int ORDER, bool CROSS>
+template <int ORDER, bool CROSS, bool TMA>
 __global__ void __launch_bounds__(NTHR, 1)
-chol_panel_kernel(MatArgs a, int j, double* X, long x_stride, int xT, CrossArgs cr, PreAcc pre) {
-    extern __shared__ __align__(16) double smem[];
+chol_panel_kernel(MatArgs a, int j, double* X, long x_stride, int xT, CrossArgs cr, PreAcc pre,
+                  const __grid_constant__ TmaMaps tm) {
+    static_assert(!(CROSS && TMA), "the prediction rows live in X, which has no tensor map");
+    extern __shared__ __align__(1024) double smem[];
     const ThreadCoord tc;
     int p, i;
     if (CROSS) { p = blockIdx.x / xT; i = blockIdx.x % xT; }
@@ -553,14 +636,20 @@ chol_panel_kernel(MatArgs a, int j, double* X, long x_stride, int xT, CrossArgs 
     double* Xp = CROSS ? X + (long)p * x_stride : a.A + (long)p * a.mat_stride;
     const double* arows = Xp + (long)i * TB * a.lda;
     const double* brows = Ap + (long)j * TB * a.lda;
-    __shared__ uint64_t bars[2 * NSTAGE];
+    __shared__ uint64_t bars[2 * NSTAGE], bars_tma[2 * NSTAGE];
     Ring ring;
-    ring_init(ring, bars);
+    ring_init(ring, bars);                 // the epilogue product's cp.async ring (and the main loop's without TMA)
     Acc acc;
     acc_zero(acc);
     if (pre.buf)
         preacc_load(acc, pre, CROSS ? (long)p * xT + i : (long)p * (a.T - j) + (i - j), j * (TB / BK), tc.tid);
-    else
+    else if (TMA) {
+        Ring ring_m;
+        ring_init_tma(ring_m, bars_tma);
+        gemm_nt_loop_tma<false>(
+            acc, [&](int kt) { return TmaSlice{&tm.A, kt * BK, p * a.lda + i * TB, &tm.A, kt * BK, p * a.lda + j * TB}; },
+            j * (TB / BK), smem, ring_m, tc);
+    } else
         gemm_nt_loop<false>(acc, [&](int kt) { return SliceSrc{arows + kt * BK, a.lda, brows + kt * BK, a.lda}; },
                             j * (TB / BK), smem, ring, tc);
 
@@ -884,15 +973,17 @@ __global__ void __launch_bounds__(NTHR) alpha_from_inverse_kernel(MatArgs a, con
 
 // ---- triangular inverse, block row i:  W_ij = -inv(L_ii) sum_{k=j}^{i-1} L_ik W_kj -----------
 // stored transposed: U[j-block rows][i-block cols] = W_ij^T (upper triangle of the pair's buffer).
-__global__ void __launch_bounds__(NTHR, 1) trtri_row_kernel(MatArgs a, int i, PreAcc pre) {
-    extern __shared__ __align__(16) double smem[];
+template <bool TMA>
+__global__ void __launch_bounds__(NTHR, 1)
+trtri_row_kernel(MatArgs a, int i, PreAcc pre, const __grid_constant__ TmaMaps tm) {
+    extern __shared__ __align__(1024) double smem[];
     const ThreadCoord tc;
     const int p = blockIdx.x / i, j = blockIdx.x % i;
     double* Ap = a.A + (long)p * a.mat_stride;
     const double* Lrow = Ap + (long)i * TB * a.lda;          // L[i-block rows][*]
     const double* Urow = Ap + (long)j * TB * a.lda;          // U[j-block rows][*]
     const double* DTj = a.DT + ((long)p * a.T + j) * (TB * TB);
-    __shared__ uint64_t bars[2 * NSTAGE];
+    __shared__ uint64_t bars[2 * NSTAGE], bars_tma[2 * NSTAGE];
     Ring ring;
     ring_init(ring, bars);
     Acc acc;
@@ -900,7 +991,18 @@ __global__ void __launch_bounds__(NTHR, 1) trtri_row_kernel(MatArgs a, int i, Pr
     // k-block j: B[n][k] = W_jj[k][n] = DT_j[n][k];  k-blocks j+1 .. i-1: B[n][k] = U[j*128+n][k]
     if (pre.buf)
         preacc_load(acc, pre, (long)p * i + j, (i - j) * (TB / BK), tc.tid);
-    else
+    else if (TMA) {
+        Ring ring_m;
+        ring_init_tma(ring_m, bars_tma);
+        gemm_nt_loop_tma<false, SKIP_B_UP>(
+            acc,
+            [&](int kt) {
+                const int ka = j * TB + kt * BK, ra = p * a.lda + i * TB;
+                return kt < TB / BK ? TmaSlice{&tm.A, ka, ra, &tm.DT, kt * BK, (p * a.T + j) * TB}
+                                    : TmaSlice{&tm.A, ka, ra, &tm.A, ka, p * a.lda + j * TB};
+            },
+            (i - j) * (TB / BK), smem, ring_m, tc);
+    } else
         gemm_nt_loop<false, SKIP_B_UP>(
             acc,
             [&](int kt) {
@@ -938,10 +1040,11 @@ __global__ void __launch_bounds__(NTHR, 1) trtri_row_kernel(MatArgs a, int i, Pr
 // Off-diagonal tiles are counted twice (symmetry).  part[p][tile][4].
 // FAM: 0 RBF (the reference), 3 / 5 Matern (dK/dlog ell from sklearn kernels.py: 3 D exp(-sqrt(3 D)) resp.
 // 5/3 D (sqrt(5 D) + 1) exp(-sqrt(5 D)), D = squared scaled distance).
-template <int FAM>
+template <int FAM, bool TMA>
 __global__ void __launch_bounds__(NTHR, 1)
-lauum_grad_kernel(MatArgs a, const double* __restrict__ alpha, double* __restrict__ part, int ntiles) {
-    extern __shared__ __align__(16) double smem[];
+lauum_grad_kernel(MatArgs a, const double* __restrict__ alpha, double* __restrict__ part, int ntiles,
+                  const __grid_constant__ TmaMaps tm) {
+    extern __shared__ __align__(1024) double smem[];
     const ThreadCoord tc;
     const int p = blockIdx.x / ntiles, q = blockIdx.x % ntiles;
     int I = (int)((sqrt(8.0 * q + 1.0) - 1.0) * 0.5);
@@ -954,12 +1057,30 @@ lauum_grad_kernel(MatArgs a, const double* __restrict__ alpha, double* __restric
     const double* DTI = a.DT + ((long)p * a.T + I) * (TB * TB);
     __shared__ uint64_t bars[2 * NSTAGE];
     Ring ring;
-    ring_init(ring, bars);
+    if (TMA) ring_init_tma(ring, bars); else ring_init(ring, bars);
     Acc acc;
     acc_zero(acc);
     // k-block I comes from the diagonal-block inverse DT_I (row stride 128), k-blocks I+1.. from U (row stride lda)
     const int nk = (a.T - I) * (TB / BK);
-    if (I == J) {
+    if (TMA) {
+        const int rI = p * a.lda + I * TB, rJ = p * a.lda + J * TB, rD = (p * a.T + I) * TB;
+        if (I == J)
+            gemm_nt_loop_tma<true, SKIP_A_UP>(
+                acc,
+                [&](int kt) {
+                    return kt < TB / BK ? TmaSlice{&tm.DT, kt * BK, rD, nullptr, 0, 0}
+                                        : TmaSlice{&tm.A, I * TB + kt * BK, rI, nullptr, 0, 0};
+                },
+                nk, smem, ring, tc);
+        else
+            gemm_nt_loop_tma<false, SKIP_A_UP>(
+                acc,
+                [&](int kt) {
+                    const int kb = I * TB + kt * BK;
+                    return kt < TB / BK ? TmaSlice{&tm.DT, kt * BK, rD, &tm.A, kb, rJ} : TmaSlice{&tm.A, kb, rI, &tm.A, kb, rJ};
+                },
+                nk, smem, ring, tc);
+    } else if (I == J) {
         gemm_nt_loop<true, SKIP_A_UP>(
             acc,
             [&](int kt) {

@@ -101,6 +101,7 @@ __device__ __forceinline__ void small_block_sum(double (&v)[NV], double* red, do
     __syncthreads();
 }
 
+#ifndef GPBO_CHOL32_ALLTHREADS
 // Cholesky of the 32 x 32 diagonal block at (o, o) of the packed matrix by warp 0 (warp_chol32, kernels_chol.cuh:
 // registers + shuffles, no barrier inside).  dinv[o + i] = 1 / L_ii.  flag: one double of scratch.  Ends with
 // __syncthreads(); returns (uniformly) whether a pivot was <= 0.  flag: 33 doubles of scratch.
@@ -113,6 +114,45 @@ __device__ __forceinline__ bool small_chol32(double* L, int o, double* dinv, dou
     __syncthreads();
     return *flag != 0.0;
 }
+#else
+// Variant kept for A/B measurements (-DGPBO_CHOL32_ALLTHREADS): all threads of the CTA, one barrier per pivot step.
+__device__ __forceinline__ bool small_chol32(double* L, int o, double* dinv, double* rsv) {
+    const int NT = blockDim.x;
+    const int TPR = NT / SB;
+    const int tid = threadIdx.x;
+    const int r = tid / TPR, cg = tid % TPR;
+    double* Lr = L + tri(o + r) + o;
+    bool bad = false;
+    for (int j = 0; j < SB - 1; ++j) {
+        double d = L[tri(o + j) + o + j];
+        if (!(d > 0.0)) { bad = true; d = 1.0; }
+        const double inv_d = __drcp_rn(d);
+        if (tid == 0) rsv[j] = d;
+        if (r > j) {
+            const double w = Lr[j] * inv_d;
+            for (int c = cg; c < SB; c += TPR)
+                if (c > j && c <= r) Lr[c] = fma(-w, L[tri(o + c) + o + j], Lr[c]);
+        }
+        __syncthreads();
+    }
+    {
+        double d = L[tri(o + SB - 1) + o + SB - 1];
+        if (!(d > 0.0)) { bad = true; d = 1.0; }
+        if (tid == 0) rsv[SB - 1] = d;
+    }
+    __syncthreads();
+    if (tid < SB) rsv[tid] = rsqrt(rsv[tid]);
+    __syncthreads();
+    for (int c = cg; c < SB; c += TPR)
+        if (c <= r) {
+            const double v = Lr[c];
+            Lr[c] = (c == r && !(v > 0.0)) ? 1.0 : v * rsv[c];
+        }
+    if (tid < SB) dinv[o + tid] = rsv[tid];
+    __syncthreads();
+    return bad;
+}
+#endif
 
 // One LML + gradient evaluation by the whole CTA.  sm: dynamic shared memory (small_smem_bytes(n)).
 // Thread 0 returns the results in out[0..3] = (lml, grad) and *st = 0 / 1 (not positive definite: lml = -inf, grad = 0),

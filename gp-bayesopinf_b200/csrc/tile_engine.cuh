@@ -20,6 +20,8 @@
 #pragma once
 #include <type_traits>
 
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace gpbo {
@@ -137,18 +139,38 @@ constexpr int SKIP_A_LO = 4;        // A[r][k] != 0 only for k <= r  (D as the r
 constexpr int SKIP_B_UP = 8;        // B[n][k] != 0 only for k >= n  (DT as the column operand)
 constexpr int SKIP_B_LO = 16;       // B[n][k] != 0 only for k <= n  (D as the column operand)
 
+// Where the four lanes c of a DMMA k-step ks read their k element inside a staged row (doubles from the row start).
+//   KoffPadded : padded cp.async rows, natural order       k = 4 ks + c           (c is folded into the base pointer)
+//   KoffSwz    : dense 128-byte TMA rows under the 128-byte swizzle, PERMUTED k  k = 8 (c >> 1) + 2 ks + (c & 1), i.e.
+//                16-byte chunk 4 (c >> 1) + ks, which the swizzle stores at chunk (4 (c >> 1) + ks) ^ (row & 7).  Both
+//                operands use the same permutation, so the contraction is unchanged; the 16 lanes of a half warp
+//                (row & 7 = g in 0..3 or 4..7, c = 0..3) hit 16 distinct 8-byte bank pairs -- conflict free without
+//                padding (tools/mma_tma.cu).
+struct KoffPadded {
+    __device__ __forceinline__ int operator()(int ks) const { return ks * 4; }
+};
+struct KoffSwz {
+    int o[BK / 4];
+    __device__ __forceinline__ KoffSwz(int g, int c) {
+#pragma unroll
+        for (int ks = 0; ks < BK / 4; ++ks) o[ks] = ((((c >> 1) * 4 + ks) ^ g) << 1) + (c & 1);
+    }
+    __device__ __forceinline__ int operator()(int ks) const { return o[ks]; }
+};
+
 // Two of the four k-steps (HALF = 0: ks 0,1; HALF = 1: ks 2,3) of DMMA on one staged pair of slices, restricted
 // to the accumulator blocks mi in [MI0, MI1), ni in [NI0, NI1).
-// sa/sb already point at this thread's first fragment element: s?[(w? * 8 + g) * stride + c].
-template <int SA_STRIDE, int SB_STRIDE, int HALF, int MI0 = 0, int MI1 = 8, int NI0 = 0, int NI1 = 4>
-__device__ __forceinline__ void mma_half(Acc& acc, const double* sa, const double* sb) {
+// sa/sb already point at this thread's first fragment element: s?[(w? * 8 + g) * stride + c] (padded rows) or
+// s?[(w? * 8 + g) * stride] (swizzled rows).
+template <int SA_STRIDE, int SB_STRIDE, int HALF, int MI0 = 0, int MI1 = 8, int NI0 = 0, int NI1 = 4, class KOFF = KoffPadded>
+__device__ __forceinline__ void mma_half(Acc& acc, const double* sa, const double* sb, const KOFF& ko = KOFF()) {
 #pragma unroll
     for (int ks = HALF * (BK / 8); ks < (HALF + 1) * (BK / 8); ++ks) {
         double a[8], b[4];
 #pragma unroll
-        for (int mi = MI0; mi < MI1; ++mi) a[mi] = sa[mi * FRAG_A_STEP * SA_STRIDE + ks * 4];
+        for (int mi = MI0; mi < MI1; ++mi) a[mi] = sa[mi * FRAG_A_STEP * SA_STRIDE + ko(ks)];
 #pragma unroll
-        for (int ni = NI0; ni < NI1; ++ni) b[ni] = sb[ni * FRAG_B_STEP * SB_STRIDE + ks * 4];
+        for (int ni = NI0; ni < NI1; ++ni) b[ni] = sb[ni * FRAG_B_STEP * SB_STRIDE + ko(ks)];
 #pragma unroll
         for (int mi = MI0; mi < MI1; ++mi)
 #pragma unroll
@@ -157,17 +179,17 @@ __device__ __forceinline__ void mma_half(Acc& acc, const double* sa, const doubl
 }
 
 // Same for a symmetric (diagonal) tile: warp (WM, WN) computes only its blocks with 4 ni + WN <= 2 mi + WM.
-template <int SA_STRIDE, int SB_STRIDE, int HALF, int WM, int WN>
-__device__ __forceinline__ void mma_half_sym(Acc& acc, const double* sa, const double* sb) {
+template <int SA_STRIDE, int SB_STRIDE, int HALF, int WM, int WN, class KOFF>
+__device__ __forceinline__ void mma_half_sym(Acc& acc, const double* sa, const double* sb, const KOFF& ko) {
 #pragma unroll
     for (int ks = HALF * (BK / 8); ks < (HALF + 1) * (BK / 8); ++ks) {
         double a[8], b[4];
 #pragma unroll
         for (int mi = 0; mi < 8; ++mi)
-            if (WN <= 2 * mi + WM) a[mi] = sa[mi * FRAG_A_STEP * SA_STRIDE + ks * 4];
+            if (WN <= 2 * mi + WM) a[mi] = sa[mi * FRAG_A_STEP * SA_STRIDE + ko(ks)];
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni)
-            if (4 * ni + WN <= 14 + WM) b[ni] = sb[ni * FRAG_B_STEP * SB_STRIDE + ks * 4];
+            if (4 * ni + WN <= 14 + WM) b[ni] = sb[ni * FRAG_B_STEP * SB_STRIDE + ko(ks)];
 #pragma unroll
         for (int mi = 0; mi < 8; ++mi)
 #pragma unroll
@@ -176,43 +198,46 @@ __device__ __forceinline__ void mma_half_sym(Acc& acc, const double* sa, const d
     }
 }
 
-template <int SA_STRIDE, int SB_STRIDE, int HALF>
-__device__ __forceinline__ void mma_half_sym_dispatch(Acc& acc, const double* sa, const double* sb, int warp) {
+template <int SA_STRIDE, int SB_STRIDE, int HALF, class KOFF = KoffPadded>
+__device__ __forceinline__ void mma_half_sym_dispatch(Acc& acc, const double* sa, const double* sb, int warp,
+                                                      const KOFF& ko = KOFF()) {
     switch (warp) {   // warp = wm * 4 + wn
-        case 0: mma_half_sym<SA_STRIDE, SB_STRIDE, HALF, 0, 0>(acc, sa, sb); break;
-        case 1: mma_half_sym<SA_STRIDE, SB_STRIDE, HALF, 0, 1>(acc, sa, sb); break;
-        case 2: mma_half_sym<SA_STRIDE, SB_STRIDE, HALF, 0, 2>(acc, sa, sb); break;
-        case 3: mma_half_sym<SA_STRIDE, SB_STRIDE, HALF, 0, 3>(acc, sa, sb); break;
-        case 4: mma_half_sym<SA_STRIDE, SB_STRIDE, HALF, 1, 0>(acc, sa, sb); break;
-        case 5: mma_half_sym<SA_STRIDE, SB_STRIDE, HALF, 1, 1>(acc, sa, sb); break;
-        case 6: mma_half_sym<SA_STRIDE, SB_STRIDE, HALF, 1, 2>(acc, sa, sb); break;
-        default: mma_half_sym<SA_STRIDE, SB_STRIDE, HALF, 1, 3>(acc, sa, sb); break;
+        case 0: mma_half_sym<SA_STRIDE, SB_STRIDE, HALF, 0, 0>(acc, sa, sb, ko); break;
+        case 1: mma_half_sym<SA_STRIDE, SB_STRIDE, HALF, 0, 1>(acc, sa, sb, ko); break;
+        case 2: mma_half_sym<SA_STRIDE, SB_STRIDE, HALF, 0, 2>(acc, sa, sb, ko); break;
+        case 3: mma_half_sym<SA_STRIDE, SB_STRIDE, HALF, 0, 3>(acc, sa, sb, ko); break;
+        case 4: mma_half_sym<SA_STRIDE, SB_STRIDE, HALF, 1, 0>(acc, sa, sb, ko); break;
+        case 5: mma_half_sym<SA_STRIDE, SB_STRIDE, HALF, 1, 1>(acc, sa, sb, ko); break;
+        case 6: mma_half_sym<SA_STRIDE, SB_STRIDE, HALF, 1, 2>(acc, sa, sb, ko); break;
+        default: mma_half_sym<SA_STRIDE, SB_STRIDE, HALF, 1, 3>(acc, sa, sb, ko); break;
     }
 }
 
 // One slice (kt = 0..7) of a k-block in which an operand is a triangular block inverse: the 8-row (8-column)
 // groups that lie entirely in its zero part are left out.  With the interleaved layout the live set is the
 // same for every warp:  A_UP: mi <= kt;   A_LO: mi >= kt;   B_UP: ni <= (2 kt + 1) / 4;   B_LO: ni >= ceil((2 kt - 3) / 4).
-template <int SA_STRIDE, int SB_STRIDE, int HALF, int KIND, int KT>
-__device__ __forceinline__ void mma_half_tri_case(Acc& acc, const double* sa, const double* sb) {
+// (The k permutation of KoffSwz stays inside the 16-wide slice, so the slice-level zero structure is the same.)
+template <int SA_STRIDE, int SB_STRIDE, int HALF, int KIND, int KT, class KOFF>
+__device__ __forceinline__ void mma_half_tri_case(Acc& acc, const double* sa, const double* sb, const KOFF& ko) {
     constexpr int MI0 = (KIND == SKIP_A_LO) ? KT : 0;
     constexpr int MI1 = (KIND == SKIP_A_UP) ? KT + 1 : 8;
     constexpr int NI0 = (KIND == SKIP_B_LO) ? (2 * KT - 3 > 0 ? (2 * KT - 3 + 3) / 4 : 0) : 0;
     constexpr int NI1 = (KIND == SKIP_B_UP) ? (2 * KT + 1) / 4 + 1 : 4;
-    mma_half<SA_STRIDE, SB_STRIDE, HALF, MI0, MI1, NI0, NI1>(acc, sa, sb);
+    mma_half<SA_STRIDE, SB_STRIDE, HALF, MI0, MI1, NI0, NI1, KOFF>(acc, sa, sb, ko);
 }
 
-template <int SA_STRIDE, int SB_STRIDE, int HALF, int KIND>
-__device__ __forceinline__ void mma_half_tri_dispatch(Acc& acc, const double* sa, const double* sb, int kt) {
+template <int SA_STRIDE, int SB_STRIDE, int HALF, int KIND, class KOFF = KoffPadded>
+__device__ __forceinline__ void mma_half_tri_dispatch(Acc& acc, const double* sa, const double* sb, int kt,
+                                                      const KOFF& ko = KOFF()) {
     switch (kt) {
-        case 0: mma_half_tri_case<SA_STRIDE, SB_STRIDE, HALF, KIND, 0>(acc, sa, sb); break;
-        case 1: mma_half_tri_case<SA_STRIDE, SB_STRIDE, HALF, KIND, 1>(acc, sa, sb); break;
-        case 2: mma_half_tri_case<SA_STRIDE, SB_STRIDE, HALF, KIND, 2>(acc, sa, sb); break;
-        case 3: mma_half_tri_case<SA_STRIDE, SB_STRIDE, HALF, KIND, 3>(acc, sa, sb); break;
-        case 4: mma_half_tri_case<SA_STRIDE, SB_STRIDE, HALF, KIND, 4>(acc, sa, sb); break;
-        case 5: mma_half_tri_case<SA_STRIDE, SB_STRIDE, HALF, KIND, 5>(acc, sa, sb); break;
-        case 6: mma_half_tri_case<SA_STRIDE, SB_STRIDE, HALF, KIND, 6>(acc, sa, sb); break;
-        default: mma_half_tri_case<SA_STRIDE, SB_STRIDE, HALF, KIND, 7>(acc, sa, sb); break;
+        case 0: mma_half_tri_case<SA_STRIDE, SB_STRIDE, HALF, KIND, 0>(acc, sa, sb, ko); break;
+        case 1: mma_half_tri_case<SA_STRIDE, SB_STRIDE, HALF, KIND, 1>(acc, sa, sb, ko); break;
+        case 2: mma_half_tri_case<SA_STRIDE, SB_STRIDE, HALF, KIND, 2>(acc, sa, sb, ko); break;
+        case 3: mma_half_tri_case<SA_STRIDE, SB_STRIDE, HALF, KIND, 3>(acc, sa, sb, ko); break;
+        case 4: mma_half_tri_case<SA_STRIDE, SB_STRIDE, HALF, KIND, 4>(acc, sa, sb, ko); break;
+        case 5: mma_half_tri_case<SA_STRIDE, SB_STRIDE, HALF, KIND, 5>(acc, sa, sb, ko); break;
+        case 6: mma_half_tri_case<SA_STRIDE, SB_STRIDE, HALF, KIND, 6>(acc, sa, sb, ko); break;
+        default: mma_half_tri_case<SA_STRIDE, SB_STRIDE, HALF, KIND, 7>(acc, sa, sb, ko); break;
     }
 }
 
@@ -256,6 +281,110 @@ __device__ __forceinline__ void gemm_nt_loop(Acc& acc, SRC src, int nk, double* 
             else
                 mma_half<LDT, LDT, H>(acc, sa, sb);
         });
+}
+
+// ---- the same main loop with TMA staging ---------------------------------------------------------------------
+// Operand slices are fetched by cp.async.bulk.tensor (SASS UTMALDG) issued by ONE thread: a 16 x 128 box of a 2-D
+// tensor map (inner dimension = k, 128-byte swizzle) lands as 128 dense 128-byte rows; the mbarrier of the stage gets
+// the byte count with arrive.expect_tx and completes when the data has landed.  The 255 other threads do nothing but
+// wait, load fragments and issue DMMAs: 97.9 % of the DMMA issue peak on the K^-1 tile product against 95.9 % for the
+// LDGSTS ring (tools/mma_tma.cu, profiles/r02b_mma_tma.txt); three stages do as well as four.
+struct TmaMaps {
+    CUtensorMap A;    // [cap * m_pad rows][m_pad]   the pairs' factor / inverse buffers
+    CUtensorMap D;    // [cap * T * 128 rows][128]   inv(L_jj)
+    CUtensorMap DT;   // [cap * T * 128 rows][128]   inv(L_jj)^T
+};
+
+// Slice kt of the two operands as tensor-map coordinates: {k, row} of the box origin.
+struct TmaSlice {
+    const CUtensorMap* ma;
+    int ka, ra;
+    const CUtensorMap* mb;
+    int kb, rb;
+};
+
+constexpr int TMA_STAGE_DBL = TB * BK;                                 // dense rows: 16 KB per operand per stage
+constexpr int TMA_MAIN_SMEM = NSTAGE * 2 * TMA_STAGE_DBL * 8;          // 131072 B
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(b);
+    asm volatile("{ .reg .b64 t; mbarrier.arrive.expect_tx.shared.b64 t, [%0], %1; }\n" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    uint32_t d = (uint32_t)__cvta_generic_to_shared(dst), b = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
+        ::"r"(d), "l"(map), "r"(c0), "r"(c1), "r"(b) : "memory");
+}
+
+// bars: 2 * NSTAGE mbarriers; full: one arrival (the producer's expect_tx) + the transaction bytes, empty: one per warp.
+__device__ __forceinline__ void ring_init_tma(Ring& r, uint64_t* bars) {
+    r.full = bars;
+    r.empty = bars + NSTAGE;
+    r.count = 0;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < NSTAGE; ++s) {
+            mbar_init(&bars[s], 1);
+            mbar_init(&bars[NSTAGE + s], NTHR / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::);
+    }
+    __syncthreads();
+}
+
+// acc += A * B^T over nk k-slices, src(kt) -> TmaSlice; SAME / TRI1 as in gemm_nt_loop.  smem must be 1024-byte aligned
+// (swizzle atom) and must not have been written through the generic proxy since the last TMA use without a
+// fence.proxy.async (it is not, in the kernels that use this: the loop runs once, first thing).
+template <bool SAME, int TRI1 = 0, class SRC>
+__device__ __forceinline__ void gemm_nt_loop_tma(Acc& acc, SRC src, int nk, double* smem, Ring& ring,
+                                                 const ThreadCoord& tc) {
+    if (nk <= 0) return;
+    double* sA = smem;
+    double* sB = smem + NSTAGE * TMA_STAGE_DBL;
+    const KoffSwz ko(tc.g, tc.c);
+    const int oa = (tc.wm * 8 + tc.g) * BK;
+    const int ob = (tc.wn * 8 + tc.g) * BK;
+    const int base = ring.count;
+    auto push = [&](int kt) {
+        const int gi = base + kt;
+        const int st = gi % NSTAGE;
+        if (gi >= NSTAGE) mbar_wait(&ring.empty[st], ((gi / NSTAGE) - 1) & 1);
+        const TmaSlice t = src(kt);
+        mbar_expect_tx(&ring.full[st], (SAME ? 1 : 2) * TMA_STAGE_DBL * 8);
+        tma_load_2d(sA + st * TMA_STAGE_DBL, t.ma, t.ka, t.ra, &ring.full[st]);
+        if (!SAME) tma_load_2d(sB + st * TMA_STAGE_DBL, t.mb, t.kb, t.rb, &ring.full[st]);
+    };
+    if (tc.tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NSTAGE - 1; ++s)
+            if (s < nk) push(s);
+    }
+    for (int kt = 0; kt < nk; ++kt) {
+        const int gi = base + kt;
+        const int cs = gi % NSTAGE;
+        const int nx = kt + NSTAGE - 1;
+        if (tc.tid == 0 && nx < nk) push(nx);        // refill of the stage consumed one slice ago, before this slice's DMMAs
+        mbar_wait(&ring.full[cs], (gi / NSTAGE) & 1);
+        const double* sa = sA + cs * TMA_STAGE_DBL + oa;
+        const double* sb = (SAME ? sA : sB) + cs * TMA_STAGE_DBL + ob;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (SAME) {
+                if (h == 0) mma_half_sym_dispatch<BK, BK, 0>(acc, sa, sb, tc.warp, ko);
+                else mma_half_sym_dispatch<BK, BK, 1>(acc, sa, sb, tc.warp, ko);
+            } else if (TRI1 != 0 && kt < TB / BK) {
+                if (h == 0) mma_half_tri_dispatch<BK, BK, 0, TRI1>(acc, sa, sb, kt, ko);
+                else mma_half_tri_dispatch<BK, BK, 1, TRI1>(acc, sa, sb, kt, ko);
+            } else {
+                if (h == 0) mma_half<BK, BK, 0, 0, 8, 0, 4>(acc, sa, sb, ko);
+                else mma_half<BK, BK, 1, 0, 8, 0, 4>(acc, sa, sb, ko);
+            }
+        }
+        __syncwarp();
+        if (tc.lane == 0) mbar_arrive(&ring.empty[cs]);
+    }
+    ring.count = base + nk;
 }
 
 // Store the accumulator tile into a shared 128x128 tile with row stride LD.
