@@ -297,16 +297,16 @@ int set_kernel_attrs() {
     if (dev >= 0 && dev < 64 && g_attr_done[dev]) return GPBO_OK;
 #define GPBO_ATTR(K, BYTES) CUDA_TRY(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES));
 #define GPBO_ATTR_ORDER(O)                                                                                          \
-    GPBO_ATTR((chol_diag_kernel<O, false>), MAIN_SMEM) GPBO_ATTR((chol_diag_kernel<O, true>), MAIN_SMEM)              \
-    GPBO_ATTR((chol_panel_kernel<O, false, false>), TILE_SMEM) GPBO_ATTR((chol_panel_kernel<O, false, true>), TILE_SMEM)
+    GPBO_ATTR((chol_diag_kernel<O, false>), MAIN_SMEM + SMEM_ALIGN_PAD) GPBO_ATTR((chol_diag_kernel<O, true>), MAIN_SMEM + SMEM_ALIGN_PAD)              \
+    GPBO_ATTR((chol_panel_kernel<O, false, false>), TILE_SMEM + SMEM_ALIGN_PAD) GPBO_ATTR((chol_panel_kernel<O, false, true>), TILE_SMEM + SMEM_ALIGN_PAD)
     GPBO_ATTR_ORDER(0) GPBO_ATTR_ORDER(1) GPBO_ATTR_ORDER(2) GPBO_ATTR_ORDER(3)
-    GPBO_ATTR((chol_panel_kernel<0, true, false>), TILE_SMEM)
-    GPBO_ATTR(trtri_row_kernel<false>, TILE_SMEM) GPBO_ATTR(trtri_row_kernel<true>, TILE_SMEM)
+    GPBO_ATTR((chol_panel_kernel<0, true, false>), TILE_SMEM + SMEM_ALIGN_PAD)
+    GPBO_ATTR(trtri_row_kernel<false>, TILE_SMEM + SMEM_ALIGN_PAD) GPBO_ATTR(trtri_row_kernel<true>, TILE_SMEM + SMEM_ALIGN_PAD)
     GPBO_ATTR(cross_sweep_kernel, TILE_SMEM)
     GPBO_ATTR(splitk_partial_kernel, MAIN_SMEM)
-    GPBO_ATTR((lauum_grad_kernel<0, false>), MAIN_SMEM) GPBO_ATTR((lauum_grad_kernel<0, true>), MAIN_SMEM)
-    GPBO_ATTR((lauum_grad_kernel<3, false>), MAIN_SMEM) GPBO_ATTR((lauum_grad_kernel<3, true>), MAIN_SMEM)
-    GPBO_ATTR((lauum_grad_kernel<5, false>), MAIN_SMEM) GPBO_ATTR((lauum_grad_kernel<5, true>), MAIN_SMEM)
+    GPBO_ATTR((lauum_grad_kernel<0, false>), MAIN_SMEM + SMEM_ALIGN_PAD) GPBO_ATTR((lauum_grad_kernel<0, true>), MAIN_SMEM + SMEM_ALIGN_PAD)
+    GPBO_ATTR((lauum_grad_kernel<3, false>), MAIN_SMEM + SMEM_ALIGN_PAD) GPBO_ATTR((lauum_grad_kernel<3, true>), MAIN_SMEM + SMEM_ALIGN_PAD)
+    GPBO_ATTR((lauum_grad_kernel<5, false>), MAIN_SMEM + SMEM_ALIGN_PAD) GPBO_ATTR((lauum_grad_kernel<5, true>), MAIN_SMEM + SMEM_ALIGN_PAD)
 #undef GPBO_ATTR_ORDER
 #undef GPBO_ATTR
     CUDA_TRY(cudaFuncSetAttribute(schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
@@ -380,8 +380,8 @@ int factor_wave(gpbo_ctx* c, cudaStream_t s, const MatArgs& a, const double* t_d
         const TmaMaps& tm = c->tmaps;
         launch(c, C_DIAG, s, [&] {
 #define GPBO_DIAG(O)                                                                          \
-    if (tma) chol_diag_kernel<O, true><<<nb, NTHR, MAIN_SMEM, s>>>(a, j, pre, tm);            \
-    else chol_diag_kernel<O, false><<<nb, NTHR, MAIN_SMEM, s>>>(a, j, pre, tm)
+    if (tma) chol_diag_kernel<O, true><<<nb, NTHR, MAIN_SMEM + SMEM_ALIGN_PAD, s>>>(a, j, pre, tm);            \
+    else chol_diag_kernel<O, false><<<nb, NTHR, MAIN_SMEM + SMEM_ALIGN_PAD, s>>>(a, j, pre, tm)
             if (gen == 0) { GPBO_DIAG(0); } else if (gen == 1) { GPBO_DIAG(1); } else if (gen == 2) { GPBO_DIAG(2); } else { GPBO_DIAG(3); }
 #undef GPBO_DIAG
         });
@@ -389,8 +389,8 @@ int factor_wave(gpbo_ctx* c, cudaStream_t s, const MatArgs& a, const double* t_d
             const int grid = nb * (a.T - 1 - j);
             launch(c, C_PANEL, s, [&] {
 #define GPBO_PANEL(O)                                                                                                   \
-    if (tma) chol_panel_kernel<O, false, true><<<grid, NTHR, TILE_SMEM, s>>>(a, j, nullptr, 0, 0, none, pre, tm);       \
-    else chol_panel_kernel<O, false, false><<<grid, NTHR, TILE_SMEM, s>>>(a, j, nullptr, 0, 0, none, pre, tm)
+    if (tma) chol_panel_kernel<O, false, true><<<grid, NTHR, TILE_SMEM + SMEM_ALIGN_PAD, s>>>(a, j, nullptr, 0, 0, none, pre, tm);       \
+    else chol_panel_kernel<O, false, false><<<grid, NTHR, TILE_SMEM + SMEM_ALIGN_PAD, s>>>(a, j, nullptr, 0, 0, none, pre, tm)
                 if (gen == 0) { GPBO_PANEL(0); } else if (gen == 1) { GPBO_PANEL(1); } else if (gen == 2) { GPBO_PANEL(2); } else { GPBO_PANEL(3); }
 #undef GPBO_PANEL
             });
@@ -418,8 +418,8 @@ int eval_wave(gpbo_ctx* c, cudaStream_t s, const double* t_dev, const double* yp
             rc = plan_split(c, s, a, 1, i, nb, i, i * (TB / BK), nullptr, 0, &pre);
             if (rc) return rc;
             launch(c, C_TRTRI, s, [&] {
-                if (c->tma_ok) trtri_row_kernel<true><<<nb * i, NTHR, TILE_SMEM, s>>>(a, i, pre, c->tmaps);
-                else trtri_row_kernel<false><<<nb * i, NTHR, TILE_SMEM, s>>>(a, i, pre, c->tmaps);
+                if (c->tma_ok) trtri_row_kernel<true><<<nb * i, NTHR, TILE_SMEM + SMEM_ALIGN_PAD, s>>>(a, i, pre, c->tmaps);
+                else trtri_row_kernel<false><<<nb * i, NTHR, TILE_SMEM + SMEM_ALIGN_PAD, s>>>(a, i, pre, c->tmaps);
             });
         }
         launch(c, C_TRSV, s, [&] { z_from_inverse_kernel<<<nb * a.T, NTHR, 0, s>>>(a, ypad, c->z.as<double>()); });
@@ -429,9 +429,9 @@ int eval_wave(gpbo_ctx* c, cudaStream_t s, const double* t_dev, const double* yp
         launch(c, C_LAUUM, s, [&] {
 #define GPBO_LAUUM(F)                                                                                                            \
     if (c->tma_ok)                                                                                                               \
-        lauum_grad_kernel<F, true><<<nb * ntiles, NTHR, MAIN_SMEM, s>>>(a, c->alpha.as<double>(), c->part.as<double>(), ntiles, c->tmaps); \
+        lauum_grad_kernel<F, true><<<nb * ntiles, NTHR, MAIN_SMEM + SMEM_ALIGN_PAD, s>>>(a, c->alpha.as<double>(), c->part.as<double>(), ntiles, c->tmaps); \
     else                                                                                                                         \
-        lauum_grad_kernel<F, false><<<nb * ntiles, NTHR, MAIN_SMEM, s>>>(a, c->alpha.as<double>(), c->part.as<double>(), ntiles, c->tmaps)
+        lauum_grad_kernel<F, false><<<nb * ntiles, NTHR, MAIN_SMEM + SMEM_ALIGN_PAD, s>>>(a, c->alpha.as<double>(), c->part.as<double>(), ntiles, c->tmaps)
             if (c->family == 0) { GPBO_LAUUM(0); } else if (c->family == 3) { GPBO_LAUUM(3); } else { GPBO_LAUUM(5); }
 #undef GPBO_LAUUM
         });
@@ -1297,7 +1297,12 @@ static int moments_device(gpbo_ctx* c, cudaStream_t s, int mode, const double* t
                 // enough row tiles to fill the GPU: one persistent launch, the sweeps cut into equal cost ranges
                 CUDA_TRY(c->sweep_flags.ensure((size_t)units * 4));
                 CUDA_TRY(cudaMemsetAsync(c->sweep_flags.p, 0, (size_t)units * 4, s));
-                const int grid = std::min(units, sm_count(c));
+                // grid: GPBO_SWEEP_MODE 0 (default): one CTA per SM, the sweeps cut along j into equal cost ranges;
+                // 1: whole units only, spread evenly (256 units -> 128 CTAs x 2, all CTAs in lock-step over j).
+                // Measured on 8 GPs x m = m' = 4096: 19.0 ms (0.78 of the DMMA peak) against 22.0 ms (0.67).
+                static const int sweep_mode = std::getenv("GPBO_SWEEP_MODE") ? std::atoi(std::getenv("GPBO_SWEEP_MODE")) : 0;
+                const int rounds = (units + sm_count(c) - 1) / sm_count(c);
+                const int grid = sweep_mode == 0 ? std::min(units, sm_count(c)) : (units + rounds - 1) / rounds;
                 launch(c, C_CROSS, s, [&] {
                     cross_sweep_kernel<<<grid, NTHR, TILE_SMEM, s>>>(a, c->X.as<double>(), xs, xT, units, crx,
                                                                      c->sweep_flags.as<int>());
@@ -1308,7 +1313,7 @@ static int moments_device(gpbo_ctx* c, cudaStream_t s, int mode, const double* t
                     rc = plan_split(c, s, a, 2, j, nb, xT, j * (TB / BK), c->X.as<double>(), xs, &pre);
                     if (rc) return rc;
                     launch(c, C_CROSS, s, [&] {
-                        chol_panel_kernel<0, true, false><<<nb * xT, NTHR, TILE_SMEM, s>>>(a, j, c->X.as<double>(), xs, xT, crx, pre, c->tmaps);
+                        chol_panel_kernel<0, true, false><<<nb * xT, NTHR, TILE_SMEM + SMEM_ALIGN_PAD, s>>>(a, j, c->X.as<double>(), xs, xT, crx, pre, c->tmaps);
                     });
                 }
             }

@@ -524,7 +524,8 @@ splitk_partial_kernel(MatArgs a, int mode, int idx, int ntile, int nsplit, int c
 template <int ORDER, bool TMA>
 __global__ void __launch_bounds__(NTHR, 1)
 chol_diag_kernel(MatArgs a, int j, PreAcc pre, const __grid_constant__ TmaMaps tm) {
-    extern __shared__ __align__(1024) double smem[];
+    extern __shared__ __align__(16) double smem_raw[];
+    double* smem = smem_align_1024(smem_raw);     // TMA's 128-byte swizzle atoms are 1024 bytes (launch: + SMEM_ALIGN_PAD)
     const ThreadCoord tc;
     const int p = blockIdx.x;
     double* Ap = a.A + (long)p * a.mat_stride;
@@ -627,7 +628,8 @@ __global__ void __launch_bounds__(NTHR, 1)
 chol_panel_kernel(MatArgs a, int j, double* X, long x_stride, int xT, CrossArgs cr, PreAcc pre,
                   const __grid_constant__ TmaMaps tm) {
     static_assert(!(CROSS && TMA), "the prediction rows live in X, which has no tensor map");
-    extern __shared__ __align__(1024) double smem[];
+    extern __shared__ __align__(16) double smem_raw[];
+    double* smem = smem_align_1024(smem_raw);     // TMA's 128-byte swizzle atoms are 1024 bytes (launch: + SMEM_ALIGN_PAD)
     const ThreadCoord tc;
     int p, i;
     if (CROSS) { p = blockIdx.x / xT; i = blockIdx.x % xT; }
@@ -778,27 +780,31 @@ cross_sweep_kernel(MatArgs a, double* X, long x_stride, int xT, int units, Cross
         }
     };
 
+    // Segments of this CTA's range, in execution order: [head of u1] [whole units] [tail of u0].  ONE call site of
+    // steps(): the body (main loop + epilogue with all their dispatch switches) is instantiated once.
+    // The host launches at most one CTA per unit, so a range covers at least one whole sweep and a unit is shared by
+    // at most two CTAs; a range strictly inside one unit (u0 == u1, j0 > 0) cannot occur and is not supported.
     const bool split_tail = j0 > 0;                                  // u0's head belongs to the previous CTA
     const bool split_head = j1 > 0 && u1 < units;                    // u1's tail belongs to the next CTA
-    if (u0 == u1) {                                                  // the whole range lies inside one unit
-        if (split_tail) {
-            if (tc.tid == 0) { while (atomicAdd(&flags[u0], 0) == 0) __nanosleep(64); __threadfence(); }
+    const int first_whole = split_tail ? u0 + 1 : u0;
+    const int n_whole = u1 > first_whole ? u1 - first_whole : 0;
+    const int nseg = (split_head ? 1 : 0) + n_whole + (split_tail ? 1 : 0);
+    for (int sidx = 0; sidx < nseg; ++sidx) {
+        const int w = sidx - (split_head ? 1 : 0);
+        const bool is_head = split_head && sidx == 0;
+        const bool is_tail = !is_head && w >= n_whole;
+        const int u = is_head ? u1 : (is_tail ? u0 : first_whole + w);
+        const int ja = is_tail ? j0 : 0, jb = is_head ? j1 : T;
+        if (is_tail) {                                               // the head was published by the previous CTA
+            if (tc.tid == 0) { while (atomicAdd(&flags[u], 0) == 0) __nanosleep(64); __threadfence(); }
             __syncthreads();
         }
-        steps(u0, j0, j1);
-        return;                                                      // (a later CTA waiting on u0's head waits on OUR predecessor)
-    }
-    if (split_head) {
-        steps(u1, 0, j1);
-        __threadfence();
-        __syncthreads();
-        if (tc.tid == 0) atomicExch(&flags[u1], 1);
-    }
-    for (int u = split_tail ? u0 + 1 : u0; u < u1; ++u) steps(u, 0, T);
-    if (split_tail) {
-        if (tc.tid == 0) { while (atomicAdd(&flags[u0], 0) == 0) __nanosleep(64); __threadfence(); }
-        __syncthreads();
-        steps(u0, j0, T);
+        steps(u, ja, jb);
+        if (is_head) {
+            __threadfence();
+            __syncthreads();
+            if (tc.tid == 0) atomicExch(&flags[u], 1);
+        }
     }
 }
 
@@ -976,7 +982,8 @@ __global__ void __launch_bounds__(NTHR) alpha_from_inverse_kernel(MatArgs a, con
 template <bool TMA>
 __global__ void __launch_bounds__(NTHR, 1)
 trtri_row_kernel(MatArgs a, int i, PreAcc pre, const __grid_constant__ TmaMaps tm) {
-    extern __shared__ __align__(1024) double smem[];
+    extern __shared__ __align__(16) double smem_raw[];
+    double* smem = smem_align_1024(smem_raw);     // TMA's 128-byte swizzle atoms are 1024 bytes (launch: + SMEM_ALIGN_PAD)
     const ThreadCoord tc;
     const int p = blockIdx.x / i, j = blockIdx.x % i;
     double* Ap = a.A + (long)p * a.mat_stride;
@@ -1044,7 +1051,8 @@ template <int FAM, bool TMA>
 __global__ void __launch_bounds__(NTHR, 1)
 lauum_grad_kernel(MatArgs a, const double* __restrict__ alpha, double* __restrict__ part, int ntiles,
                   const __grid_constant__ TmaMaps tm) {
-    extern __shared__ __align__(1024) double smem[];
+    extern __shared__ __align__(16) double smem_raw[];
+    double* smem = smem_align_1024(smem_raw);     // TMA's 128-byte swizzle atoms are 1024 bytes (launch: + SMEM_ALIGN_PAD)
     const ThreadCoord tc;
     const int p = blockIdx.x / ntiles, q = blockIdx.x % ntiles;
     int I = (int)((sqrt(8.0 * q + 1.0) - 1.0) * 0.5);

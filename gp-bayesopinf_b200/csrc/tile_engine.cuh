@@ -303,6 +303,14 @@ struct TmaSlice {
     int kb, rb;
 };
 
+// The dynamic shared window starts right after the kernel's static shared variables, at whatever offset that is:
+// kernels that stage with TMA round their base up to 1024 bytes themselves and are launched with SMEM_ALIGN_PAD extra.
+constexpr int SMEM_ALIGN_PAD = 1024;
+__device__ __forceinline__ double* smem_align_1024(double* raw) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(raw);
+    return reinterpret_cast<double*>(reinterpret_cast<char*>(raw) + ((1024u - (a & 1023u)) & 1023u));
+}
+
 constexpr int TMA_STAGE_DBL = TB * BK;                                 // dense rows: 16 KB per operand per stage
 constexpr int TMA_MAIN_SMEM = NSTAGE * 2 * TMA_STAGE_DBL * 8;          // 131072 B
 
