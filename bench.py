@@ -274,15 +274,16 @@ def main():
     total_flops_dom = flops_third * local_evals        # all launches of that class over the timed region, this rank
     dom_ms = prof[dom][0] + (prof["chol_diag"][0] if dom == "chol_panel" else 0.0)      # potrf = diag + panel
     achieved = total_flops_dom / (max(dom_ms, 1e-9) * 1e-3) / 1e12
-    traffic = None
+    traffic = traffic_launch = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dom)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        traffic, traffic_launch = tj.get(dom), tj.get("_launch", {}).get(dom)
     except Exception:
         pass
     kernel_total_ms = sum(v[0] for v in prof.values())
     roofline = {
         "bound": "tensor", "kernel": dom, "achieved": achieved, "peak": dmma_peak, "unit": "TFLOP/s",
-        "frac": achieved / dmma_peak, "traffic": traffic,
+        "frac": achieved / dmma_peak, "traffic": traffic, "traffic_launch": traffic_launch,
         "peak_source": "FP64 DMMA issue-rate micro-benchmark run in this process (gpbo_bench_dmma_peak); "
                        "MEASURED_PEAKS.json holds no FP64 figure; cuBLAS DGEMM rate beside it in dgemm_cublas_tflops",
         "peak_runs": [round(x, 3) for x in dmma_runs],
@@ -314,6 +315,7 @@ def main():
                    "sharding": "replicated optimiser pool; live pairs re-cut into N equal slices every round; "
                                "all-gather of [lml, grad] (32 B / pair) over NCCL" if world > 1 else "single GPU",
                    "l2": "inputs larger than L2 (each pair's 512 MiB factor streams from HBM)",
+                   "staging": "TMA (cp.async.bulk.tensor)" if not os.environ.get("GPBO_NO_TMA") else "LDGSTS (GPBO_NO_TMA)",
                    "waves_per_round_per_rank": -(-(-(-max(live) // world)) // max(ctx.wave_capacity(m), 1)) if live else 0,
                    "warmup_rounds": f"{max(W, 1)} rounds of {nwarm} pairs (one wave) before the timed region"},
         "clocks": clocks, "gpu_launches": int(launches),
@@ -475,16 +477,17 @@ def assembly_roofline(ctx, dev):
     res = {}
 
     def run(kind, t1, t2, th, o, n1, n2, B, reps):
+        # kernel time = the library's own CUDA events around each launch on the launching stream (gpbo_assemble
+        # synchronises the stream before it returns, which an outer pair of events would count as kernel time)
         a = (kind, t1.data_ptr(), n1, n1, t2.data_ptr(), n2, n2, th.data_ptr(), B, o.data_ptr(), stream.cuda_stream)
         ctx.assemble_device(*a)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize(dev)
-        e0.record(stream)
+        ctx.profile_enable(True)
         for _ in range(reps):
             ctx.assemble_device(*a)
-        e1.record(stream)
-        torch.cuda.synchronize(dev)
-        return reps * B * n1 * n2 * 8 / (e0.elapsed_time(e1) * 1e-3) / 1e9
+        ms, launches = ctx.profile_get()["assemble"]
+        ctx.profile_enable(False)
+        return launches * B * n1 * n2 * 8 / (ms * 1e-3) / 1e9
 
     for label, B, n1, n2, reps in (("8x8192x8192", 8, 8192, 8192, 3), ("2x16384x16384", 2, 16384, 16384, 3),
                                    ("64x3200x200", 64, 3200, 200, 20)):

@@ -242,6 +242,10 @@ MatArgs mat_args(gpbo_ctx* c, int m, int m_pad) {
     a.status = c->status.as<int>();
     a.pp = c->pp.as<PairParams>();
     a.ts = c->ts.as<double>();
+    // trtri rows launch their tiles longest-first: -2.4 % trtri time at 148 pairs, -1.6 % at 256 (m = 8192,
+    // profiles/r02c_trtri_order.txt); GPBO_TRTRI_LPT=0 restores the pair-major order
+    static const int order_flags = std::getenv("GPBO_TRTRI_LPT") ? std::atoi(std::getenv("GPBO_TRTRI_LPT")) : 1;
+    a.flags = order_flags;
     return a;
 }
 
@@ -891,13 +895,9 @@ static int assemble_impl(gpbo_ctx* c, int fam, int kind, const double* t1, long 
         const int nt = (n1 + SYM_T - 1) / SYM_T;
         dim3 gs(nt * (nt + 1) / 2, B);
         dim3 gg((n2 + ASM_COLS - 1) / ASM_COLS, (n1 + ASM_ROWS - 1) / ASM_ROWS, B);
-        // short second dimension: the flat kernel (one contiguous array, every thread busy whatever n2 is)
-        const bool flat = !sym && n2 >= FLAT_MIN_N2 && n2 <= FLAT_MAX_N2;
-        dim3 gf((unsigned)((os + FLAT_E - 1) / FLAT_E), B);
 #define GPBO_ASM_CASE(F, K)                                                                                              \
     case K:                                                                                                              \
         if (sym) assemble_sym_kernel<F, K><<<gs, NTHR, SYM_SMEM, s>>>(t1, t1_stride, n1, theta, out, os);                \
-        else if (flat) assemble_flat_kernel<F, K><<<gf, NTHR, 0, s>>>(t1, t1_stride, n1, t2, t2_stride, n2, theta, out, os); \
         else assemble_general_kernel<F, K><<<gg, NTHR, 0, s>>>(t1, t1_stride, n1, t2, t2_stride, n2, theta, out, os);    \
         break;
 #define GPBO_ASM_FAM(F)                                                                                                  \

@@ -28,6 +28,7 @@ struct MatArgs {
     int* status;        // [cap]      0 ok, 1 = not positive definite
     const PairParams* pp;   // [cap]
     const double* ts;   // [cap][m_pad] scaled abscissae t/ell (sklearn order) or raw t (rbf_eval order)
+    int flags;          // bit 0: trtri rows launch their tiles longest-first (j-major) instead of pair-major
 };
 
 // ---- element generators ("assemblers") ---------------------------------------------------
@@ -985,7 +986,11 @@ trtri_row_kernel(MatArgs a, int i, PreAcc pre, const __grid_constant__ TmaMaps t
     extern __shared__ __align__(16) double smem_raw[];
     double* smem = smem_align_1024(smem_raw);     // TMA's 128-byte swizzle atoms are 1024 bytes (launch: + SMEM_ALIGN_PAD)
     const ThreadCoord tc;
-    const int p = blockIdx.x / i, j = blockIdx.x % i;
+    // tile (p, j) has a k-loop of i - j blocks.  Pair-major order keeps the i tiles of a pair (which share the L row
+    // block) together; longest-first (flags bit 0) leaves only the short tiles for the tail of the launch.
+    int p, j;
+    if (a.flags & 1) { const int nb = gridDim.x / i; j = blockIdx.x / nb; p = blockIdx.x % nb; }
+    else { p = blockIdx.x / i; j = blockIdx.x % i; }
     double* Ap = a.A + (long)p * a.mat_stride;
     const double* Lrow = Ap + (long)i * TB * a.lda;          // L[i-block rows][*]
     const double* Urow = Ap + (long)j * TB * a.lda;          // U[j-block rows][*]

@@ -284,63 +284,10 @@ assemble_general_kernel(const double* __restrict__ t1, long t1_stride, int n1, c
     }
 }
 
-// Flat kernel for matrices with a short second dimension (the reference's own m' >> m shape, e.g. 3200 x 200): the
-// 32 x 512 tiles of the general kernel would leave most threads without a column, so the row-major output is
-// treated as ONE contiguous array: a CTA owns FLAT_E consecutive elements, every thread writes 16-byte pairs that
-// are 512 elements apart (fully coalesced whatever n2 is), row / column indices advance incrementally (no division
-// in the loop), and the scaled abscissae of the rows the chunk touches and of all n2 columns are staged in shared
-// memory once per CTA.
-constexpr int FLAT_E = 8192;          // elements per CTA
-constexpr int FLAT_MAX_N2 = 2048;     // columns staged in shared memory
-constexpr int FLAT_MIN_N2 = 8;        // below this a chunk would span more rows than the row buffer holds
-constexpr int FLAT_ROWS = FLAT_E / FLAT_MIN_N2 + 2;
-
-template <int FAM, int KIND>
-__global__ void __launch_bounds__(NTHR)
-assemble_flat_kernel(const double* __restrict__ t1, long t1_stride, int n1, const double* __restrict__ t2,
-                     long t2_stride, int n2, const double* __restrict__ theta, double* __restrict__ out,
-                     long out_stride) {
-    __shared__ double x1s[FLAT_ROWS];
-    __shared__ double x2s[FLAT_MAX_N2];
-    const int p = blockIdx.y;
-    const AsmConsts k(theta + 3 * p);
-    constexpr bool scaled = AsmScaled<FAM, KIND>::value;
-    constexpr bool has_diag = (KIND == 0 || KIND == 1);
-    const long total = (long)n1 * n2;
-    const long e0 = (long)blockIdx.x * FLAT_E;
-    const long e1 = e0 + FLAT_E < total ? e0 + FLAT_E : total;
-    const int r_first = (int)(e0 / n2), r_last = (int)((e1 - 1) / n2);
-    const double* a1 = t1 + (long)p * t1_stride;
-    const double* a2 = t2 + (long)p * t2_stride;
-    for (int i = threadIdx.x; i <= r_last - r_first; i += NTHR) {
-        const double v = a1[r_first + i];
-        x1s[i] = scaled ? v / k.ell : v;
-    }
-    for (int i = threadIdx.x; i < n2; i += NTHR) {
-        const double v = a2[i];
-        x2s[i] = scaled ? v / k.ell : v;
-    }
-    __syncthreads();
-    double* o = out + (long)p * out_stride;
-    const bool vec = (reinterpret_cast<uintptr_t>(o) & 15) == 0;      // e0 and the pair offsets are even
-    long e = e0 + 2 * threadIdx.x;
-    int r = (int)(e / n2), c = (int)(e - (long)r * n2);
-    const int dr = (2 * NTHR) / n2, dc = (2 * NTHR) % n2;
-    for (; e < e1; e += 2 * NTHR) {
-        const double va = assemble_element<FAM, KIND>(k, has_diag && r == c, x1s[r - r_first], x2s[c]);
-        int r2 = r, c2 = c + 1;
-        if (c2 == n2) { c2 = 0; ++r2; }
-        if (e + 1 < e1) {
-            const double vb = assemble_element<FAM, KIND>(k, has_diag && r2 == c2, x1s[r2 - r_first], x2s[c2]);
-            if (vec) *reinterpret_cast<double2*>(o + e) = make_double2(va, vb);
-            else { o[e] = va; o[e + 1] = vb; }
-        } else {
-            o[e] = va;
-        }
-        r += dr; c += dc;
-        if (c >= n2) { c -= n2; ++r; }
-    }
-}
+// (Two special kernels for matrices with a short second dimension -- the reference's m' >> m shape 3200 x 200 -- were
+// measured and dropped: a "flat" one treating the output as one contiguous array and a "narrow" one arranging the
+// threads as row groups x column pairs reach 0.43-0.56 of the copy peak on 64 such matrices against 0.50-0.54 for the
+// general kernel; 328 MB is written in ~100 us, the launch ramp and tail dominate -- profiles/r02c_asm_ab.txt.)
 
 constexpr int SYM_T = 64;            // tile edge of the symmetric kernel
 constexpr int SYM_LD = SYM_T + 1;    // odd stride: conflict-free row and column access
