@@ -297,3 +297,39 @@ def test_prediction_sweep_many_row_tiles(ctx):
         m0, s0 = orc.np_predict(t, y[gi], th[gi], t_est)
         assert rel(mean[gi], m0) <= 1e-10
         assert rel(std[gi], s0) <= 1e-7
+
+
+# ------------------------------------------------------------------ both staging paths of the tile engine
+def test_ldgsts_staging_matches_tma_staging(ctx):
+    """The main loops stage their operands with TMA by default and with LDGSTS under GPBO_NO_TMA=1 (read once per
+    process, so the second path runs in a child process).  Both against the oracle at 1e-10, and against each other:
+    the k permutation of the TMA fragments changes the summation order inside a 16-wide slice only."""
+    if ctx.path != "blocked":
+        pytest.skip("blocked path only")
+    import subprocess
+    import sys
+    import tempfile
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    t, y = orc.synthetic_trajectories(2, 700, seed=9)
+    theta = np.log(np.array([[2.5, 0.05, 1e-2], [0.7, 0.3, 3e-3], [1.1, 0.08, 1e-3]]))
+    gp_of = np.array([0, 1, 1], dtype=np.int32)
+    T = np.tile(t, (2, 1))
+    lml, grad, st = ctx.lml_grad(T, y, theta, gp_of)
+    with tempfile.TemporaryDirectory() as tmp:
+        np.savez(os.path.join(tmp, "in.npz"), T=T, y=y, theta=theta, gp_of=gp_of)
+        code = (
+            "import sys, numpy as np; sys.path.insert(0, %r); from gpbo_pkg import pkg; "
+            "d = np.load(%r); c = pkg.default_context(0); c.set_small_path(0); "
+            "l, g, s = c.lml_grad(d['T'], d['y'], d['theta'], d['gp_of']); np.savez(%r, l=l, g=g, s=s)"
+        ) % (root, os.path.join(tmp, "in.npz"), os.path.join(tmp, "out.npz"))
+        env = dict(os.environ, GPBO_NO_TMA="1")
+        subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=600)
+        o = np.load(os.path.join(tmp, "out.npz"))
+    assert np.all(st == 0) and np.all(o["s"] == 0)
+    for b in range(3):
+        l0, g0, _ = orc.np_lml_grad(t, y[gp_of[b]], theta[b])
+        for l1, g1 in ((lml[b], grad[b]), (o["l"][b], o["g"][b])):
+            assert abs(l1 - l0) <= 1e-10 * abs(l0)
+            assert np.all(np.abs(g1 - g0) <= 1e-9 * max(1.0, np.abs(g0).max()))
+        record("lml_rel[tma vs ldgsts staging]", abs(lml[b] - o["l"][b]) / abs(l0))
