@@ -15,7 +15,12 @@
  * OpenMP-parallel; memory 2 * m^2 * 16 bytes.
  */
 #include <math.h>
+#ifdef _OPENMP
 #include <omp.h>
+#else /* built without OpenMP (a compiler lacking libgomp): serial, same results */
+static inline int omp_get_num_threads(void) { return 1; }
+static inline int omp_get_thread_num(void) { return 0; }
+#endif
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
