@@ -481,6 +481,7 @@ def assembly_roofline(ctx, dev):
         # synchronises the stream before it returns, which an outer pair of events would count as kernel time)
         a = (kind, t1.data_ptr(), n1, n1, t2.data_ptr(), n2, n2, th.data_ptr(), B, o.data_ptr(), stream.cuda_stream)
         ctx.assemble_device(*a)
+        ctx.assemble_device(*a)
         torch.cuda.synchronize(dev)
         ctx.profile_enable(True)
         for _ in range(reps):
@@ -489,12 +490,26 @@ def assembly_roofline(ctx, dev):
         ctx.profile_enable(False)
         return launches * B * n1 * n2 * 8 / (ms * 1e-3) / 1e9
 
-    for label, B, n1, n2, reps in (("8x8192x8192", 8, 8192, 8192, 3), ("2x16384x16384", 2, 16384, 16384, 3),
-                                   ("64x3200x200", 64, 3200, 200, 20)):
+    def fill_rate(o, reps=10):
+        # write-only streaming rate of the same buffer (cudaMemset through torch): context for the 8 B / element bound
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        o.zero_()
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(reps):
+            o.zero_()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return reps * o.numel() * 8 / (e0.elapsed_time(e1) * 1e-3) / 1e9
+
+    fills = {}
+    for label, B, n1, n2, reps in (("8x8192x8192", 8, 8192, 8192, 10), ("2x16384x16384", 2, 16384, 16384, 10),
+                                   ("64x3200x200", 64, 3200, 200, 30)):
         t1 = torch.sort(torch.rand(B, n1, dtype=torch.float64, device=dev), dim=1).values.contiguous()
         t2 = t1.clone() if n1 == n2 else torch.sort(torch.rand(B, n2, dtype=torch.float64, device=dev), dim=1).values.contiguous()
         th = torch.log(torch.tensor([[1.5, 0.05, 1e-2]], dtype=torch.float64, device=dev)).repeat(B, 1).contiguous()
         o = torch.empty((B, n1, n2), dtype=torch.float64, device=dev)
+        fills[label] = round(fill_rate(o) / peak, 4)
         for kind in range(7):
             if n1 != n2 and kind in (0, 1, 5, 6):
                 continue                      # square-only kinds
@@ -507,7 +522,11 @@ def assembly_roofline(ctx, dev):
     fr = [v for v in res.values()]
     return {"bound": "hbm", "unit": "fraction of peak GB/s", "peak": peak, "bytes_per_element": 8,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy bandwidth)" if peaks else "fallback 6543.1 GB/s",
-            "min_frac": min(fr), "frac": res}
+            "min_frac": min(fr), "min_frac_square": min(v for k, v in res.items() if "3200" not in k), "frac": res,
+            "memset_frac": fills,
+            "note": "frac = 8 B x elements / kernel time (library CUDA events, mean of 10-30 launches) / copy peak; "
+                    "memset_frac = cudaMemset of the same buffer against the same peak (a write-only stream runs above "
+                    "the read+write copy figure on these boxes)"}
 
 
 def prediction_roofline(pkg, ctx, dmma_peak, G=8, m=4096):

@@ -126,6 +126,77 @@ GPBO_HD double gpbo_exp_neg(double x) {
 #endif
 }
 
+// Table-driven variant for the stand-alone assembly kernels (kernels_predict.cuh), which are FP64-issue bound:
+// exp(x) = 2^(k/64) * exp(r), k = rint(64 x / ln 2), |r| <= ln2/128 = 5.4e-3, so a degree-5 Taylor polynomial is exact
+// to 3.5e-17 relative and the whole exponential costs 10 FP64-pipe instructions instead of 16; the 64 correctly rounded
+// values 2^(j/64) come from a table the kernel copies into shared memory (an LDS, not an FP64 slot).
+// |error| <= 1.5 ulp for -708 <= x <= 0 (measured on the host: tests/test_fastmath.py), results below
+// 2^-1021 flushed to 0 like gpbo_exp_neg, exp(0) = 1 exactly.  `tab` is GPBO_EXP2_TAB or a shared-memory copy of it.
+#define GPBO_EXP2_TAB_VALUES                                                                      \
+    0x1.0000000000000p+0, 0x1.02c9a3e778061p+0, 0x1.059b0d3158574p+0, 0x1.0874518759bc8p+0,        \
+    0x1.0b5586cf9890fp+0, 0x1.0e3ec32d3d1a2p+0, 0x1.11301d0125b51p+0, 0x1.1429aaea92de0p+0,        \
+    0x1.172b83c7d517bp+0, 0x1.1a35beb6fcb75p+0, 0x1.1d4873168b9aap+0, 0x1.2063b88628cd6p+0,        \
+    0x1.2387a6e756238p+0, 0x1.26b4565e27cddp+0, 0x1.29e9df51fdee1p+0, 0x1.2d285a6e4030bp+0,        \
+    0x1.306fe0a31b715p+0, 0x1.33c08b26416ffp+0, 0x1.371a7373aa9cbp+0, 0x1.3a7db34e59ff7p+0,        \
+    0x1.3dea64c123422p+0, 0x1.4160a21f72e2ap+0, 0x1.44e086061892dp+0, 0x1.486a2b5c13cd0p+0,        \
+    0x1.4bfdad5362a27p+0, 0x1.4f9b2769d2ca7p+0, 0x1.5342b569d4f82p+0, 0x1.56f4736b527dap+0,        \
+    0x1.5ab07dd485429p+0, 0x1.5e76f15ad2148p+0, 0x1.6247eb03a5585p+0, 0x1.6623882552225p+0,        \
+    0x1.6a09e667f3bcdp+0, 0x1.6dfb23c651a2fp+0, 0x1.71f75e8ec5f74p+0, 0x1.75feb564267c9p+0,        \
+    0x1.7a11473eb0187p+0, 0x1.7e2f336cf4e62p+0, 0x1.82589994cce13p+0, 0x1.868d99b4492edp+0,        \
+    0x1.8ace5422aa0dbp+0, 0x1.8f1ae99157736p+0, 0x1.93737b0cdc5e5p+0, 0x1.97d829fde4e50p+0,        \
+    0x1.9c49182a3f090p+0, 0x1.a0c667b5de565p+0, 0x1.a5503b23e255dp+0, 0x1.a9e6b5579fdbfp+0,        \
+    0x1.ae89f995ad3adp+0, 0x1.b33a2b84f15fbp+0, 0x1.b7f76f2fb5e47p+0, 0x1.bcc1e904bc1d2p+0,        \
+    0x1.c199bdd85529cp+0, 0x1.c67f12e57d14bp+0, 0x1.cb720dcef9069p+0, 0x1.d072d4a07897cp+0,        \
+    0x1.d5818dcfba487p+0, 0x1.da9e603db3285p+0, 0x1.dfc97337b9b5fp+0, 0x1.e502ee78b3ff6p+0,        \
+    0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0
+// 1.5 * 2^52, 64 / ln 2, -(ln 2 / 64) hi / lo, Taylor coefficients 1/120, 1/24, 1/6, 1/2
+#define GPBO_EXPT_VALUES                                                                                         \
+    6755399441055744.0, 92.33248261689366, -0.010830424696249145, -3.623510646634843e-19,                       \
+    8.3333333333333332e-03, 4.1666666666666664e-02, 1.6666666666666666e-01, 0.5
+#if defined(__CUDACC__)
+static __device__ __constant__ double GPBO_EXP2_TAB[64] = {GPBO_EXP2_TAB_VALUES};
+static __device__ __constant__ double GPBO_EXPT[8] = {GPBO_EXPT_VALUES};
+#endif
+
+GPBO_HD double gpbo_exp_neg_tab(double x, const double* tab) {
+#if defined(__CUDA_ARCH__)
+    const double t = fma(x, GPBO_EXPT[1], GPBO_EXPT[0]);
+    const double k = t - GPBO_EXPT[0];
+    double r = fma(k, GPBO_EXPT[2], x);
+    r = fma(k, GPBO_EXPT[3], r);
+    const int ki = __double2loint(t);
+    const double tj = tab[ki & 63];
+    const double r2 = r * r;
+    double p = fma(r, GPBO_EXPT[4], GPBO_EXPT[5]);
+    p = fma(p, r, GPBO_EXPT[6]);
+    p = fma(p, r, GPBO_EXPT[7]);
+    const double v = fma(tj, fma(p, r2, r), tj);          // 2^(j/64) (1 + (r + r^2 (1/2 + r/6 + r^2/24 + r^3/120)))
+    const int hi = __double2hiint(v) + ((ki >> 6) << 20);
+    const int lo = __double2loint(v);
+    const bool flush = (unsigned)(__double2hiint(x) & 0x7fffffff) > 0x40862000u;     // |x| > 708 (or NaN / inf)
+    return __hiloint2double(flush ? 0 : hi, flush ? 0 : lo);
+#else
+    static const double C[8] = {GPBO_EXPT_VALUES};
+    const double t = fma(x, C[1], C[0]);
+    const double k = t - C[0];
+    double r = fma(k, C[2], x);
+    r = fma(k, C[3], r);
+    const int64_t tb = f64_bits(t), xb = f64_bits(x);
+    const int32_t ki = (int32_t)(uint32_t)(tb & 0xffffffffLL);
+    const double r2 = r * r;
+    double p = fma(r, C[4], C[5]);
+    p = fma(p, r, C[6]);
+    p = fma(p, r, C[7]);
+    const double tj = tab[ki & 63];
+    const double v = fma(tj, fma(p, r2, r), tj);
+    const int64_t vb = f64_bits(v);
+    const int32_t hi = (int32_t)(uint32_t)((uint64_t)vb >> 32) + (int32_t)((uint32_t)(ki >> 6) << 20);
+    const uint32_t lo = (uint32_t)(vb & 0xffffffffLL);
+    const bool flush = ((uint32_t)((uint64_t)xb >> 32) & 0x7fffffffu) > 0x40862000u;
+    return flush ? 0.0 : bits_f64((int64_t)(((uint64_t)(uint32_t)hi << 32) | lo));
+#endif
+}
+
 GPBO_HD double gpbo_div(double a, double b, double rb) {
     const double q = a * rb;
     const double e = fma(-q, b, a);

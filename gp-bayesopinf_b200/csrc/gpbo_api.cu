@@ -87,6 +87,7 @@ struct gpbo_ctx {
     DevBuf wp_lhs, wp_rhs, wp_olhs, wp_orhs;
     // split-K partial tiles (small batches)
     DevBuf pre;
+    DevBuf asm_consts, asm_xs;  // per-matrix constants / scaled abscissae of the stand-alone assembly (asm_prep_kernel)
     // TMA tensor maps of the wave buffers (A, D, DT), re-encoded when a buffer moves or the padded size changes
     TmaMaps tmaps;
     const void* tm_A = nullptr; const void* tm_D = nullptr; const void* tm_DT = nullptr;
@@ -315,11 +316,6 @@ int set_kernel_attrs() {
 #undef GPBO_ATTR
     CUDA_TRY(cudaFuncSetAttribute(schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(ns_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAIN_SMEM));
-#define GPBO_SYM_ATTR(F, K) CUDA_TRY(cudaFuncSetAttribute(assemble_sym_kernel<F, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, SYM_SMEM));
-#define GPBO_SYM_ATTR_F(F) GPBO_SYM_ATTR(F, 0) GPBO_SYM_ATTR(F, 1) GPBO_SYM_ATTR(F, 2) GPBO_SYM_ATTR(F, 3) GPBO_SYM_ATTR(F, 4) GPBO_SYM_ATTR(F, 5) GPBO_SYM_ATTR(F, 6)
-    GPBO_SYM_ATTR_F(0) GPBO_SYM_ATTR_F(3) GPBO_SYM_ATTR_F(5)
-#undef GPBO_SYM_ATTR_F
-#undef GPBO_SYM_ATTR
     if (dev >= 0 && dev < 64) g_attr_done[dev] = true;
     return GPBO_OK;
 }
@@ -812,7 +808,8 @@ int gpbo_destroy(gpbo_ctx* c) {
                       &c->X, &c->trow, &c->tsrc, &c->out1, &c->out2, &c->cov_dev,
                       &c->nsY, &c->nsZ, &c->nsT, &c->nsTT, &c->nsYn, &c->nsZn, &c->nsPart, &c->nsNorm, &c->nsResid, &c->w_dev,
                       &c->pre, &c->wp_lhs, &c->wp_rhs, &c->wp_olhs, &c->wp_orhs,
-                      &c->sm_counter, &c->sm_starts, &c->sm_theta, &c->sm_fun, &c->sm_ints, &c->sm_dbg};
+                      &c->sm_counter, &c->sm_starts, &c->sm_theta, &c->sm_fun, &c->sm_ints, &c->sm_dbg, &c->asm_consts, &c->asm_xs,
+                      &c->sweep_flags, &c->kzz_tab, &c->kzz_flag};
     for (DevBuf* b : bufs) b->release();
     for (auto& r : c->recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -891,14 +888,29 @@ static int assemble_impl(gpbo_ctx* c, int fam, int kind, const double* t1, long 
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const long os = (long)n1 * n2;
     const bool sym = (t1 == t2 && t1_stride == t2_stride && n1 == n2);
+    if ((kind == 0 || kind == 1) && n1 != n2) return fail(GPBO_EINVAL, "assemble: the train kinds 0 / 1 need n1 == n2");
+    const bool scaled = fam != 0 || kind == 0 || kind == 2 || kind == 6;       // AsmScaled: the generator works on t / ell
+    CUDA_TRY(c->asm_consts.ensure((size_t)B * sizeof(AsmConsts)));
+    if (scaled) CUDA_TRY(c->asm_xs.ensure((size_t)B * ((size_t)n1 + (sym ? 0 : n2)) * 8));
+    const AsmConsts* kc = c->asm_consts.as<AsmConsts>();
+    double* xs1 = c->asm_xs.as<double>();
+    double* xs2 = sym ? xs1 : xs1 + (size_t)B * n1;
+    const double* a1 = scaled ? xs1 : t1;
+    const double* a2 = scaled ? xs2 : t2;
+    const long s1 = scaled ? n1 : t1_stride, s2 = scaled ? n2 : t2_stride;
+    // threads per CTA of the general kernel: one per column pair, 64 ... 256
+    const int gthr = std::min(NTHR, std::max(64, ((n2 + 1) / 2 + 31) / 32 * 32));
     launch(c, C_ASM, s, [&] {
+        asm_prep_kernel<<<dim3((std::max(n1, n2) + 255) / 256, B), 256, 0, s>>>(theta, t1, t1_stride, n1, t2, t2_stride, n2,
+                                                                                scaled, sym, c->asm_consts.as<AsmConsts>(),
+                                                                                xs1, xs2);
         const int nt = (n1 + SYM_T - 1) / SYM_T;
         dim3 gs(nt * (nt + 1) / 2, B);
-        dim3 gg((n2 + ASM_COLS - 1) / ASM_COLS, (n1 + ASM_ROWS - 1) / ASM_ROWS, B);
+        dim3 gg((n2 + 2 * gthr - 1) / (2 * gthr), (n1 + ASM_ROWS - 1) / ASM_ROWS, B);
 #define GPBO_ASM_CASE(F, K)                                                                                              \
     case K:                                                                                                              \
-        if (sym) assemble_sym_kernel<F, K><<<gs, NTHR, SYM_SMEM, s>>>(t1, t1_stride, n1, theta, out, os);                \
-        else assemble_general_kernel<F, K><<<gg, NTHR, 0, s>>>(t1, t1_stride, n1, t2, t2_stride, n2, theta, out, os);    \
+        if (sym) assemble_sym2_kernel<F, K><<<gs, NTHR, SYM2_SMEM, s>>>(a1, s1, n1, kc, out, os);                        \
+        else assemble_general_kernel<F, K><<<gg, gthr, 0, s>>>(a1, s1, n1, a2, s2, n2, kc, out, os);                     \
         break;
 #define GPBO_ASM_FAM(F)                                                                                                  \
     switch (kind) { GPBO_ASM_CASE(F, 0) GPBO_ASM_CASE(F, 1) GPBO_ASM_CASE(F, 2) GPBO_ASM_CASE(F, 3) GPBO_ASM_CASE(F, 4)   \
@@ -906,6 +918,7 @@ static int assemble_impl(gpbo_ctx* c, int fam, int kind, const double* t1, long 
         if (fam == 0) { GPBO_ASM_FAM(0) } else if (fam == 3) { GPBO_ASM_FAM(3) } else { GPBO_ASM_FAM(5) }
 #undef GPBO_ASM_FAM
 #undef GPBO_ASM_CASE
+        if (!sym && (kind == 0 || kind == 1)) asm_diag_kernel<<<dim3((n1 + 255) / 256, B), 256, 0, s>>>(kc, n1, out, os);
     });
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(s));

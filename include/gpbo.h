@@ -74,7 +74,8 @@ int gpbo_wave_capacity(gpbo_ctx* ctx, int m);
  * 1244-1296, 1374-1419, 1530-1587) and the NumPy broadcasting of gpkernels.py:591-609, 630-641.
  * kind: 0 K(theta)=sigma^2 R+chi I (sklearn order)   1 K_yy (rbf_eval order)   2 K(t1,t2) sklearn cross
  *       3 kappa(t1,t2)   4 K_zy=d/dt1 kappa   5 K_zz=d2/dt1dt2 kappa   6 dK/dlog(ell)
- * t1: [B][n1] with stride t1_stride (0 = shared), t2 likewise; theta [B][3]; out [B][n1][n2]. */
+ * t1: [B][n1] with stride t1_stride (0 = shared), t2 likewise; theta [B][3]; out [B][n1][n2].  The train kinds 0 / 1
+ * (white noise on the diagonal, sklearn `kernel_(X)`) need n1 == n2 (GPBO_EINVAL otherwise). */
 int gpbo_assemble(gpbo_ctx* ctx, int kind, const double* t1, long t1_stride, int n1, const double* t2,
                   long t2_stride, int n2, const double* theta, int B, double* out, void* stream);
 

@@ -43,8 +43,23 @@ SRC = textwrap.dedent(r'''
             if (gpbo::gpbo_exp_neg(y) != gpbo::gpbo_exp(y)) ++neq;
         }
         if (gpbo::gpbo_exp_neg(0.0) != 1.0 || gpbo::gpbo_exp_neg(-1e9) != 0.0 || gpbo::gpbo_exp_neg(-INFINITY) != 0.0) ++neq;
-        std::printf("%.6f %ld %ld %.3f %d %d %ld\n", maxulp, bad, ndiff, maxd, gpbo::gpbo_exp(0.0) == 1.0,
-                    std::isnan(gpbo::gpbo_exp(NAN)) ? 1 : 0, neq);
+        // the table-driven variant of the stand-alone assembly kernels (10 FP64 instructions): <= 1.5 ulp on [-708, 0]
+        static const double TAB[64] = {GPBO_EXP2_TAB_VALUES};
+        double tabulp = 0; long tabbad = 0;
+        auto check_tab = [&](double x) {
+            const double y = gpbo::gpbo_exp_neg_tab(x, TAB);
+            if (x < -708.0005) { if (y != 0.0) ++tabbad; return; }
+            if (x < -708.0) return;                                     // either flushed or not: both accepted
+            const long double ref = expl((long double)x);
+            const double refd = (double)ref;
+            const double ulp = std::nextafter(refd, INFINITY) - refd;
+            tabulp = std::fmax(tabulp, std::fabs((double)((long double)y - ref)) / ulp);
+        };
+        for (long i = 0; i < 2000000; ++i) { check_tab(U(rng)); check_tab(V(rng)); check_tab(W(rng)); check_tab(Z(rng)); }
+        if (gpbo::gpbo_exp_neg_tab(0.0, TAB) != 1.0 || gpbo::gpbo_exp_neg_tab(-1e9, TAB) != 0.0 ||
+            gpbo::gpbo_exp_neg_tab(-INFINITY, TAB) != 0.0) ++tabbad;
+        std::printf("%.6f %ld %ld %.3f %d %d %ld %.6f %ld\n", maxulp, bad, ndiff, maxd, gpbo::gpbo_exp(0.0) == 1.0,
+                    std::isnan(gpbo::gpbo_exp(NAN)) ? 1 : 0, neq, tabulp, tabbad);
     }
 ''')
 
@@ -63,3 +78,4 @@ def test_fast_exp_and_div_error(tmp_path):
     assert bad == 0              # exact 0 below the flush threshold
     assert ndiff <= 20 and maxd <= 1.0   # division correctly rounded up to rare 1-ulp cases
     assert exp0 == 1 and nan_ok == 1
+    assert float(out[7]) <= 1.5 and int(out[8]) == 0      # table-driven exp of the assembly kernels
