@@ -86,7 +86,12 @@ struct gpbo_ctx {
     int w_G = 0, w_n = 0;            // shape of the sqrtW stack currently resident in w_dev
     DevBuf wp_lhs, wp_rhs, wp_olhs, wp_orhs;
     // split-K partial tiles (small batches)
-    DevBuf pre;
+    DevBuf pre, pre2;             // pre2: partials of the inverse rows when they run on the side stream
+    // side stream + events: in the latency-bound regime (few pairs) the inverse rows W = L^-1 run in the shadow of the
+    // factorisation's dependency chain (eval_wave)
+    cudaStream_t side = nullptr;
+    std::vector<cudaEvent_t> diag_events;
+    cudaEvent_t side_done = nullptr;
     DevBuf asm_consts, asm_xs;  // per-matrix constants / scaled abscissae of the stand-alone assembly (asm_prep_kernel)
     // TMA tensor maps of the wave buffers (A, D, DT), re-encoded when a buffer moves or the padded size changes
     TmaMaps tmaps;
@@ -324,9 +329,12 @@ int set_kernel_attrs() {
 // is cut into up to 16 chunks of >= 4 slices computed by separate CTAs (splitk_partial_kernel) first.
 // Returns a PreAcc with buf == nullptr when the fused kernels should run their own loop.
 int plan_split(gpbo_ctx* c, cudaStream_t s, const MatArgs& a, int mode, int idx, int nb, int ntile, int nk_max,
-               const double* X, long x_stride, PreAcc* out) {
+               const double* X, long x_stride, PreAcc* out, DevBuf* prebuf = nullptr) {
+    if (!prebuf) prebuf = &c->pre;
+    // partials of the side stream (prebuf == pre2) fill only 1/div of the SMs, the rest stays free for the chain
+    static const int side_div = std::getenv("GPBO_SIDE_SPLIT_DIV") ? std::max(1, std::atoi(std::getenv("GPBO_SIDE_SPLIT_DIV"))) : 1;
     out->buf = nullptr; out->nsplit = 1; out->chunk = nk_max;
-    const int g_sm_count = sm_count(c);
+    const int g_sm_count = prebuf == &c->pre2 ? std::max(1, sm_count(c) / side_div) : sm_count(c);
     const long units = (long)nb * ntile;
     if (units <= 0 || nk_max < 16) return GPBO_OK;
     // tuning knobs (defaults measured on B200): at most SPLIT_MAX chunks of at least SPLIT_MIN slices
@@ -350,12 +358,12 @@ int plan_split(gpbo_ctx* c, cudaStream_t s, const MatArgs& a, int mode, int idx,
     if (nsplit < 2) return GPBO_OK;
     const int chunk = (nk_max + nsplit - 1) / nsplit;
     nsplit = (nk_max + chunk - 1) / chunk;
-    CUDA_TRY(c->pre.ensure((size_t)units * nsplit * 64 * NTHR * 8));
+    CUDA_TRY(prebuf->ensure((size_t)units * nsplit * 64 * NTHR * 8));
     launch(c, mode == 1 ? C_TRTRI : (mode == 2 ? C_CROSS : C_PANEL), s, [&] {
         splitk_partial_kernel<<<(unsigned)(units * nsplit), NTHR, MAIN_SMEM, s>>>(a, mode, idx, ntile, nsplit, chunk,
-                                                                                 c->pre.as<double>(), X, x_stride);
+                                                                                 prebuf->as<double>(), X, x_stride);
     });
-    out->buf = c->pre.as<double>(); out->nsplit = nsplit; out->chunk = chunk;
+    out->buf = prebuf->as<double>(); out->nsplit = nsplit; out->chunk = chunk;
     return GPBO_OK;
 }
 
@@ -364,7 +372,8 @@ int plan_split(gpbo_ctx* c, cudaStream_t s, const MatArgs& a, int mode, int idx,
 // solve_alpha = false: neither z = L^-1 y nor alpha is computed (the caller gets both from the inverse factor after
 // trtri: z_from_inverse_kernel, alpha_from_inverse_kernel).
 int factor_wave(gpbo_ctx* c, cudaStream_t s, const MatArgs& a, const double* t_dev, const double* ypad,
-                const double* theta_dev, const int* gpof_dev, int nb, int order, bool solve_alpha = true) {
+                const double* theta_dev, const int* gpof_dev, int nb, int order, bool solve_alpha = true,
+                const cudaEvent_t* diag_events = nullptr) {
     const int gen = c->family == 0 ? order : (c->family == 3 ? 2 : 3);     // element generator (AsmSelect index)
     if (c->family != 0) order = 0;
     launch(c, C_PREP, s, [&] {
@@ -385,6 +394,7 @@ int factor_wave(gpbo_ctx* c, cudaStream_t s, const MatArgs& a, const double* t_d
             if (gen == 0) { GPBO_DIAG(0); } else if (gen == 1) { GPBO_DIAG(1); } else if (gen == 2) { GPBO_DIAG(2); } else { GPBO_DIAG(3); }
 #undef GPBO_DIAG
         });
+        if (diag_events) CUDA_TRY(cudaEventRecord(diag_events[j], s));      // L row j, D_j, DT_j are final
         if (j < a.T - 1) {
             const int grid = nb * (a.T - 1 - j);
             launch(c, C_PANEL, s, [&] {
@@ -409,18 +419,47 @@ int eval_wave(gpbo_ctx* c, cudaStream_t s, const double* t_dev, const double* yp
               int* status) {
     MatArgs a = mat_args(c, m, m_pad);
     update_tma_maps(c, m_pad);
-    int rc = factor_wave(c, s, a, t_dev, ypad, theta_dev, gpof_dev, nb, 0, !with_grad);
+    // Few pairs in flight: the factorisation is a chain of T dependent (partials -> diagonal block -> panel) steps that
+    // leaves most SMs idle, and row i of W = L^-1 needs only what exists once diagonal block i is done -- so the inverse
+    // rows run on a side stream, each behind the event of "its" diagonal block, in the shadow of the chain (single pair,
+    // m = 4096: 9.9 -> ~7 ms per evaluation; the optimiser's tail is a sequence of such evaluations).  With many pairs
+    // every launch fills the GPU and the two streams would only compete, so the rows stay on the main stream.
+    static const int overlap_max = std::getenv("GPBO_OVERLAP_MAX") ? std::atoi(std::getenv("GPBO_OVERLAP_MAX")) : 48;
+    const bool overlap = with_grad && nb <= overlap_max && a.T >= 4;
+    if (overlap) {
+        if (!c->side) {
+            // lowest priority: its CTAs take an SM only when the factorisation chain (on the handle's own stream: highest
+            // priority) has none waiting
+            int least = 0, greatest = 0;
+            CUDA_TRY(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+            CUDA_TRY(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, least));
+        }
+        if (!c->side_done) CUDA_TRY(cudaEventCreateWithFlags(&c->side_done, cudaEventDisableTiming));
+        while ((int)c->diag_events.size() < a.T) {
+            cudaEvent_t e;
+            CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            c->diag_events.push_back(e);
+        }
+    }
+    int rc = factor_wave(c, s, a, t_dev, ypad, theta_dev, gpof_dev, nb, 0, !with_grad,
+                         overlap ? c->diag_events.data() : nullptr);
     if (rc) return rc;
     const int ntiles = a.T * (a.T + 1) / 2;
     if (with_grad) {
+        cudaStream_t st = overlap ? c->side : s;
         for (int i = 1; i < a.T; ++i) {
+            if (overlap) CUDA_TRY(cudaStreamWaitEvent(st, c->diag_events[i], 0));
             PreAcc pre;
-            rc = plan_split(c, s, a, 1, i, nb, i, i * (TB / BK), nullptr, 0, &pre);
+            rc = plan_split(c, st, a, 1, i, nb, i, i * (TB / BK), nullptr, 0, &pre, overlap ? &c->pre2 : nullptr);
             if (rc) return rc;
-            launch(c, C_TRTRI, s, [&] {
-                if (c->tma_ok) trtri_row_kernel<true><<<nb * i, NTHR, TILE_SMEM + SMEM_ALIGN_PAD, s>>>(a, i, pre, c->tmaps);
-                else trtri_row_kernel<false><<<nb * i, NTHR, TILE_SMEM + SMEM_ALIGN_PAD, s>>>(a, i, pre, c->tmaps);
+            launch(c, C_TRTRI, st, [&] {
+                if (c->tma_ok) trtri_row_kernel<true><<<nb * i, NTHR, TILE_SMEM + SMEM_ALIGN_PAD, st>>>(a, i, pre, c->tmaps);
+                else trtri_row_kernel<false><<<nb * i, NTHR, TILE_SMEM + SMEM_ALIGN_PAD, st>>>(a, i, pre, c->tmaps);
             });
+        }
+        if (overlap) {
+            CUDA_TRY(cudaEventRecord(c->side_done, st));
+            CUDA_TRY(cudaStreamWaitEvent(s, c->side_done, 0));
         }
         launch(c, C_TRSV, s, [&] { z_from_inverse_kernel<<<nb * a.T, NTHR, 0, s>>>(a, ypad, c->z.as<double>()); });
         launch(c, C_TRSV, s, [&] {
@@ -794,7 +833,11 @@ int gpbo_create(gpbo_ctx** out, int device, size_t max_workspace_bytes) {
     gpbo_ctx* c = new gpbo_ctx();
     c->device = device;
     c->limit = max_workspace_bytes;
-    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    {
+        int least = 0, greatest = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        CUDA_TRY(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, greatest));
+    }
     *out = c;
     return GPBO_OK;
 }
@@ -807,7 +850,7 @@ int gpbo_destroy(gpbo_ctx* c) {
                       &c->t_dev, &c->y_dev, &c->ypad, &c->theta_dev, &c->gpof_dev, &c->lml_dev, &c->grad_dev, &c->st_dev,
                       &c->X, &c->trow, &c->tsrc, &c->out1, &c->out2, &c->cov_dev,
                       &c->nsY, &c->nsZ, &c->nsT, &c->nsTT, &c->nsYn, &c->nsZn, &c->nsPart, &c->nsNorm, &c->nsResid, &c->w_dev,
-                      &c->pre, &c->wp_lhs, &c->wp_rhs, &c->wp_olhs, &c->wp_orhs,
+                      &c->pre, &c->pre2, &c->wp_lhs, &c->wp_rhs, &c->wp_olhs, &c->wp_orhs,
                       &c->sm_counter, &c->sm_starts, &c->sm_theta, &c->sm_fun, &c->sm_ints, &c->sm_dbg, &c->asm_consts, &c->asm_xs,
                       &c->sweep_flags, &c->kzz_tab, &c->kzz_flag};
     for (DevBuf* b : bufs) b->release();
@@ -819,6 +862,9 @@ int gpbo_destroy(gpbo_ctx* c) {
     if (c->h_lml) cudaFreeHost(c->h_lml);
     if (c->h_grad) cudaFreeHost(c->h_grad);
     if (c->h_gpof) cudaFreeHost(c->h_gpof);
+    for (cudaEvent_t e : c->diag_events) cudaEventDestroy(e);
+    if (c->side_done) cudaEventDestroy(c->side_done);
+    if (c->side) cudaStreamDestroy(c->side);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return GPBO_OK;

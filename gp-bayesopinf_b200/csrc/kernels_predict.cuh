@@ -330,7 +330,8 @@ assemble_general_kernel(const double* __restrict__ x1, long x1_stride, int n1, c
 // (Two special kernels for matrices with a short second dimension -- the reference's m' >> m shape 3200 x 200 -- were
 // measured and dropped in round 2b: a "flat" one treating the output as one contiguous array and a "narrow" one arranging
 // the threads as row groups x column pairs, profiles/r02c_asm_ab.txt.  What that shape needed was less work outside the
-// element loop -- the pre-pass above -- and a CTA no wider than the matrix.)
+// element loop -- the pre-pass above -- and a CTA no wider than the matrix.  A CTA sweeping several row blocks (set-up
+// once per CTA instead of once per 32 rows) spills at the 32-register cap and runs at 0.45-0.60: dropped, same file.)
 
 // Symmetric kernel (t1 is t2: train matrices, K_zz, dK/dlog ell): only tiles I >= J (64 x 64) are evaluated -- half the
 // FP64 work.  The DIRECT tile is stored straight from the registers that computed it (thread (ty, tx) owns rows
