@@ -7,10 +7,11 @@ as ``gp_bayesopinf_b200``.
 Public surface (mirrors the reference):
   gpkernels.GP_RBFW                      -- drop-in for codebase/gpkernels.py::GP_RBFW (sklearn path)
   step2_fitgps.fit_gaussian_processes    -- batched drop-in for */step2_fitgps.py
+  step3_posterior.posterior_grid         -- posterior means / precisions of step 3 for a grid of regularizers (N3)
   _lib.Context                           -- ctypes handle on libgpbo.so (C ABI in include/gpbo.h)
 """
 
-from . import _lib, gpkernels, sharding, step2_fitgps, workload  # noqa: F401
+from . import _lib, gpkernels, sharding, step2_fitgps, step3_posterior, workload  # noqa: F401
 from ._lib import Context, GpboError, default_context  # noqa: F401
 from .gpkernels import GP_MaternW, GP_RBFW  # noqa: F401
 from .step2_fitgps import fit_gaussian_processes, fit_gaussian_processes_multi  # noqa: F401

@@ -28,7 +28,7 @@ EXPORTS = (
     "gpbo_lstsq_weights_host", "gpbo_assemble_matern", "gpbo_set_kernel_family",
     "gpbo_weighted_products_host", "gpbo_set_small_path", "gpbo_optpool_create", "gpbo_optpool_destroy",
     "gpbo_optpool_live", "gpbo_optpool_feed", "gpbo_optpool_result", "gpbo_problem_upload_host",
-    "gpbo_lml_grad_resident_host", "gpbo_get_stream",
+    "gpbo_lml_grad_resident_host", "gpbo_get_stream", "gpbo_posterior_grid_host",
 )
 
 
@@ -77,6 +77,8 @@ def load():
     lib.gpbo_lstsq_weights_host.argtypes = [vp, dp, dp, C.c_int, C.c_int, dp, dp, C.c_long, C.c_int, C.c_double, dp, dp,
                                             dp, dp, ip, ip, ip]
     lib.gpbo_weighted_products_host.argtypes = [vp, dp, C.c_int, C.c_int, dp, C.c_int, dp, dp, dp]
+    lib.gpbo_posterior_grid_host.argtypes = [vp, dp, C.c_int, C.c_int, dp, C.c_int, dp, dp, C.c_int, dp, dp, dp, dp,
+                                             C.POINTER(C.c_int)]
     lib.gpbo_set_small_path.argtypes = [vp, C.c_int]
     lib.gpbo_get_stream.argtypes = [vp, C.POINTER(vp)]
     lib.gpbo_optpool_create.argtypes = [C.POINTER(vp), C.c_int, dp, dp, dp]
@@ -405,6 +407,36 @@ class Context:
         _check(self._lib.gpbo_weighted_products_host(self._h, _dp(w), G, n, _dp(lhs), d, _dp(rhs), _dp(out_lhs),
                                                      _dp(out_rhs)), "gpbo_weighted_products_host")
         return out_lhs, out_rhs
+
+    def posterior_grid(self, lhs, rhs, regularizers, sqrtW=None, want_chol=True):
+        """Step-3 posterior assembly for a grid of regularizers (PDEs/step3_estimate.py:75-95 for every candidate of
+        :131-146): per GP g and regularizer k the posterior mean of the operator row, the Cholesky factor of its
+        precision ``(sqrtW_g D)^T (sqrtW_g D) + reg_k^2 I`` and whether that precision is positive definite.
+        sqrtW=None: the weight matrices resident on the device since the last lstsq_weights / sqrtw call.
+        -> dict(means (K, G, d), chol (K, G, d, d) | None, gram (G, d, d), proj (G, d), status (K, G))."""
+        lhs = _f64(lhs)
+        rhs = _f64(np.atleast_2d(rhs))
+        regs = _f64(np.atleast_1d(regularizers))
+        G, n = rhs.shape
+        if lhs.ndim != 2 or lhs.shape[0] != n:
+            raise ValueError(f"expected lhs.shape == ({n}, d)")
+        d = lhs.shape[1]
+        if regs.ndim != 1 or regs.size == 0 or not np.all(np.isfinite(regs)):
+            raise ValueError("regularizers must be a non-empty 1-D array of finite values")
+        w = None
+        if sqrtW is not None:
+            w = _f64(sqrtW)
+            if w.shape != (G, n, n):
+                raise ValueError(f"expected sqrtW.shape == ({G}, {n}, {n})")
+        K = regs.size
+        means = np.empty((K, G, d))
+        chol = np.empty((K, G, d, d)) if want_chol else None
+        gram, proj = np.empty((G, d, d)), np.empty((G, d))
+        status = np.empty((K, G), dtype=np.int32)
+        _check(self._lib.gpbo_posterior_grid_host(self._h, _dp(w), G, n, _dp(lhs), d, _dp(rhs), _dp(regs), K, _dp(means),
+                                                  _dp(chol), _dp(gram), _dp(proj), _ip(status)),
+               "gpbo_posterior_grid_host")
+        return {"means": means, "chol": chol, "gram": gram, "proj": proj, "status": status}
 
     # -- device-pointer entry points (torch tensors are only address carriers) ------------
     def assemble_device(self, kind, t1_ptr, t1_stride, n1, t2_ptr, t2_stride, n2, theta_ptr, B, out_ptr, stream=0,

@@ -11,6 +11,7 @@
 
 #include "kernels_predict.cuh"
 #include "kernels_sqrtw.cuh"
+#include "kernels_posterior.cuh"
 #include "kernels_small.cuh"
 #include "lbfgsb.h"
 
@@ -85,6 +86,7 @@ struct gpbo_ctx {
     DevBuf nsY, nsZ, nsT, nsTT, nsYn, nsZn, nsPart, nsNorm, nsResid, w_dev;
     int w_G = 0, w_n = 0;            // shape of the sqrtW stack currently resident in w_dev
     DevBuf wp_lhs, wp_rhs, wp_olhs, wp_orhs;
+    DevBuf pg_gram, pg_proj, pg_regs, pg_means, pg_chol, pg_status, pg_tmp;      // posterior grid (kernels_posterior.cuh)
     // split-K partial tiles (small batches)
     DevBuf pre, pre2;             // pre2: partials of the inverse rows when they run on the side stream
     // side stream + events: in the latency-bound regime (few pairs) the inverse rows W = L^-1 run in the shadow of the
@@ -850,7 +852,7 @@ int gpbo_destroy(gpbo_ctx* c) {
                       &c->t_dev, &c->y_dev, &c->ypad, &c->theta_dev, &c->gpof_dev, &c->lml_dev, &c->grad_dev, &c->st_dev,
                       &c->X, &c->trow, &c->tsrc, &c->out1, &c->out2, &c->cov_dev,
                       &c->nsY, &c->nsZ, &c->nsT, &c->nsTT, &c->nsYn, &c->nsZn, &c->nsPart, &c->nsNorm, &c->nsResid, &c->w_dev,
-                      &c->pre, &c->pre2, &c->wp_lhs, &c->wp_rhs, &c->wp_olhs, &c->wp_orhs,
+                      &c->pre, &c->pre2, &c->pg_gram, &c->pg_proj, &c->pg_regs, &c->pg_means, &c->pg_chol, &c->pg_status, &c->pg_tmp, &c->wp_lhs, &c->wp_rhs, &c->wp_olhs, &c->wp_orhs,
                       &c->sm_counter, &c->sm_starts, &c->sm_theta, &c->sm_fun, &c->sm_ints, &c->sm_dbg, &c->asm_consts, &c->asm_xs,
                       &c->sweep_flags, &c->kzz_tab, &c->kzz_flag};
     for (DevBuf* b : bufs) b->release();
@@ -1530,6 +1532,68 @@ int gpbo_weighted_products_host(gpbo_ctx* c, const double* sqrtw, int G, int n, 
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(out_lhs, c->wp_olhs.p, (size_t)G * n * d * 8, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(out_rhs, c->wp_orhs.p, (size_t)G * n * 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return GPBO_OK;
+}
+
+int gpbo_posterior_grid_host(gpbo_ctx* c, const double* sqrtw, int G, int n, const double* lhs, int d, const double* rhs,
+                             const double* regs, int nreg, double* means, double* chol, double* gram, double* proj,
+                             int* status) {
+    if (!c || !lhs || !rhs || !regs || !means || !status || G <= 0 || n <= 0 || d <= 0 || nreg <= 0)
+        return fail(GPBO_EINVAL, "posterior_grid_host: bad argument");
+    if (d > POST_DMAX) return fail(GPBO_EINVAL, "posterior_grid_host: operator rows longer than 128 entries are not supported");
+    for (int k = 0; k < nreg; ++k)
+        if (!std::isfinite(regs[k])) return fail(GPBO_EINVAL, "posterior_grid_host: non-finite regularizer");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    if (sqrtw) {
+        CUDA_TRY(c->w_dev.ensure((size_t)G * n * n * 8));
+        CUDA_TRY(cudaMemcpyAsync(c->w_dev.p, sqrtw, (size_t)G * n * n * 8, cudaMemcpyHostToDevice, s));
+        c->w_G = G; c->w_n = n;
+    } else if (c->w_G != G || c->w_n != n || !c->w_dev.p) {
+        return fail(GPBO_EINVAL, "posterior_grid_host: sqrtw is NULL but the resident weight stack has another shape "
+                                 "(call gpbo_lstsq_weights_host / gpbo_sqrtw_host for the same G, n first)");
+    }
+    const size_t slots = (size_t)nreg * G;
+    CUDA_TRY(c->wp_lhs.ensure((size_t)n * d * 8));
+    CUDA_TRY(c->wp_rhs.ensure((size_t)G * n * 8));
+    CUDA_TRY(c->wp_olhs.ensure((size_t)G * n * d * 8));
+    CUDA_TRY(c->wp_orhs.ensure((size_t)G * n * 8));
+    CUDA_TRY(c->pg_gram.ensure((size_t)G * d * d * 8));
+    CUDA_TRY(c->pg_proj.ensure((size_t)G * d * 8));
+    CUDA_TRY(c->pg_regs.ensure((size_t)nreg * 8));
+    CUDA_TRY(c->pg_means.ensure(slots * d * 8));
+    if (chol) CUDA_TRY(c->pg_chol.ensure(slots * d * d * 8));
+    CUDA_TRY(c->pg_status.ensure(slots * 4));
+    CUDA_TRY(c->pg_tmp.ensure(slots * n * 8));
+    CUDA_TRY(cudaMemcpyAsync(c->wp_lhs.p, lhs, (size_t)n * d * 8, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(c->wp_rhs.p, rhs, (size_t)G * n * 8, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(c->pg_regs.p, regs, (size_t)nreg * 8, cudaMemcpyHostToDevice, s));
+    const size_t smem = ((size_t)d * (d + 1) + 3 * (size_t)d + 8) * 8;
+    CUDA_TRY(cudaFuncSetAttribute(ridge_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    launch(c, C_SQRTW, s, [&] {
+        weighted_products_kernel<<<dim3((n + NTHR / 32 - 1) / (NTHR / 32), G), NTHR, 0, s>>>(
+            c->w_dev.as<double>(), n, c->wp_lhs.as<double>(), d, c->wp_rhs.as<double>(), c->wp_olhs.as<double>(),
+            c->wp_orhs.as<double>());
+    });
+    const int nt = (d + GRAM_T - 1) / GRAM_T;
+    launch(c, C_SQRTW, s, [&] {
+        gram_kernel<<<dim3(nt * nt, G), 256, 0, s>>>(c->wp_olhs.as<double>(), c->wp_orhs.as<double>(), n, d,
+                                                      c->pg_gram.as<double>(), c->pg_proj.as<double>());
+    });
+    launch(c, C_SQRTW, s, [&] {
+        ridge_solve_kernel<<<dim3(G, nreg), 256, smem, s>>>(c->wp_olhs.as<double>(), c->wp_orhs.as<double>(), n, d,
+                                                            c->pg_gram.as<double>(), c->pg_proj.as<double>(),
+                                                            c->pg_regs.as<double>(), c->pg_means.as<double>(),
+                                                            chol ? c->pg_chol.as<double>() : nullptr,
+                                                            c->pg_status.as<int>(), c->pg_tmp.as<double>());
+    });
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(means, c->pg_means.p, slots * d * 8, cudaMemcpyDeviceToHost, s));
+    if (chol) CUDA_TRY(cudaMemcpyAsync(chol, c->pg_chol.p, slots * d * d * 8, cudaMemcpyDeviceToHost, s));
+    if (gram) CUDA_TRY(cudaMemcpyAsync(gram, c->pg_gram.p, (size_t)G * d * d * 8, cudaMemcpyDeviceToHost, s));
+    if (proj) CUDA_TRY(cudaMemcpyAsync(proj, c->pg_proj.p, (size_t)G * d * 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(status, c->pg_status.p, slots * 4, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     return GPBO_OK;
 }

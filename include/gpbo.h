@@ -190,6 +190,24 @@ int gpbo_lstsq_weights_host(gpbo_ctx* ctx, const double* t, const double* y, int
 int gpbo_weighted_products_host(gpbo_ctx* ctx, const double* sqrtw, int G, int n, const double* lhs, int d,
                                 const double* rhs, double* out_lhs, double* out_rhs);
 
+/* Posterior assembly of step 3 for a grid of regularizers (the linear algebra of
+ * PDEs/step3_estimate.py:75-95 = get_bayesian_model(reg), for all candidates of the grid search :131-146 at once).
+ * For every GP / mode g and every regularizer regs[k]:
+ *   A_g = sqrtW[g] @ lhs, b_g = sqrtW[g] @ rhs[g]          (codebase/wlstsq.py:183-188)
+ *   gram[g] = A_g^T A_g, proj[g] = A_g^T b_g;  precision P = gram[g] + regs[k]^2 I      (step3_estimate.py:86-90)
+ *   means[k][g] = argmin |A_g o - b_g|^2 + regs[k]^2 |o|^2  (lstsq_solver.solve(), :78-79; opinf L2Solver)
+ *   chol[k][g]  = lower Cholesky factor of P -- what scipy.stats.Covariance.from_precision computes inside
+ *                 bayes.BayesianROM (codebase/bayes.py:283-287); status[k][g] = 1 when P is not positive definite
+ *                 (the reference's LinAlgError "Matrix is not positive definite" -> candidate skipped, :92-95;
+ *                 means[k][g] is then NaN), else 0.
+ * All pointers HOST.  sqrtw [G][n][n] or NULL (use the stack resident from gpbo_lstsq_weights_host / gpbo_sqrtw_host,
+ * same G and n); lhs [n][d] with d <= 128; rhs [G][n]; regs [nreg]; means [nreg][G][d]; chol [nreg][G][d][d] or NULL;
+ * gram [G][d][d] or NULL; proj [G][d] or NULL; status [nreg][G].  Integrating the ROM for the posterior draws of each
+ * candidate (the rest of the grid search) needs `opinf` and stays in the reference. */
+int gpbo_posterior_grid_host(gpbo_ctx* ctx, const double* sqrtw, int G, int n, const double* lhs, int d, const double* rhs,
+                             const double* regs, int nreg, double* means, double* chol, double* gram, double* proj,
+                             int* status);
+
 /* Per-kernel-class device timing (CUDA events on the launching stream), for bench.py's roofline.
  * Classes: 0 prep 1 chol_diag 2 chol_panel 3 trsv 4 trtri 5 lauum_grad 6 finalize 7 cross_panel
  *          8 schur 9 mean_std (fused kernel-row x alpha means) 10 assemble 11 sqrtw 12 small (in-shared path)

@@ -387,3 +387,36 @@ def synthetic_trajectories(r, m, seed=0):
     y = (a[:, :, None] * np.sin(2 * np.pi * f[:, :, None] * t[None, None, :] + ph[:, :, None])).sum(1)
     y += 0.03 * rng.standard_normal((r, m))
     return t, y
+
+
+def np_posterior_grid(sqrtW, D, rhs, regs):
+    """CPU restatement of the step-3 posterior assembly for a grid of regularizers (PARITY UNPINNED:
+    the reference's step 3 cannot run here because `opinf` (requirements.txt: opinf==0.5.9) is not installed).
+    Follows PDEs/step3_estimate.py:75-95 with codebase/wlstsq.py:183-188:
+      A_i = sqrtW_i @ D, b_i = sqrtW_i @ rhs_i                                  (wlstsq.py:183-188)
+      mean = opinf.lstsq.L2Solver(reg).fit(A_i, b_i).solve(): the SVD route of opinf 0.5.9,
+             V diag(s / (s^2 + reg^2)) U^T b                                   (published algorithm, un-vendored)
+      precision = A_i^T A_i + reg^2 I                                           (step3_estimate.py:86-90)
+      status = 1 where np.linalg.cholesky(precision) fails -- scipy.stats.Covariance.from_precision inside
+               bayes.BayesianROM (bayes.py:283-287) raises "Matrix is not positive definite" there.
+    -> means (K, r, d), chol (K, r, d, d), gram (r, d, d), proj (r, d), status (K, r)."""
+    import numpy as np
+
+    sqrtW, D, rhs = np.asarray(sqrtW, float), np.asarray(D, float), np.atleast_2d(np.asarray(rhs, float))
+    regs = np.atleast_1d(np.asarray(regs, float))
+    r, d, K = sqrtW.shape[0], D.shape[1], regs.size
+    means, chol = np.empty((K, r, d)), np.zeros((K, r, d, d))
+    gram, proj, status = np.empty((r, d, d)), np.empty((r, d)), np.zeros((K, r), dtype=np.int32)
+    for i in range(r):
+        A = sqrtW[i] @ D
+        b = sqrtW[i] @ rhs[i]
+        gram[i], proj[i] = A.T @ A, A.T @ b
+        U, s, Vt = np.linalg.svd(A, full_matrices=False)
+        Utb = U.T @ b
+        for k, reg in enumerate(regs):
+            means[k, i] = Vt.T @ ((s / (s**2 + reg**2)) * Utb)
+            try:
+                chol[k, i] = np.linalg.cholesky(gram[i] + reg**2 * np.eye(d))
+            except np.linalg.LinAlgError:
+                status[k, i] = 1
+    return {"means": means, "chol": chol, "gram": gram, "proj": proj, "status": status}
