@@ -346,6 +346,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_extras:
         extras = (("evals_configs3", 25.0, lambda: evals_configs3(pkg, ctx, dev, dmma_peak)),
                   ("roofline_prediction", 15.0, lambda: prediction_roofline(pkg, ctx, dmma_peak)),
+                  ("posterior_grid", 5.0, lambda: posterior_grid_sample(ctx)),
                   ("roofline_assembly", 15.0, lambda: assembly_roofline(ctx, dev)),
                   ("dgemm_cublas_tflops", 3.0, lambda: dgemm_rate(dev)),
                   ("fit_reference_configs", 10.0, lambda: fit_reference_configs(ctx)),
@@ -579,6 +580,31 @@ def prediction_roofline(pkg, ctx, dmma_peak, G=8, m=4096):
             "sqrtw_iterations": int(wit.max()), "sqrtw_status_ok": int((wst == 0).sum()),
             "sqrtw_ms": prof["sqrtw"][0], "sqrtw_identity_residual": resid,
             "sqrtw_dmma_issued_tflops": tf(ns_flops, prof["sqrtw"][0])}
+
+
+def posterior_grid_sample(ctx, d=45, nreg=81):
+    """Step-3 posterior assembly for the 8 weight matrices left resident by prediction_roofline (m' = 4096):
+    posterior means, precisions and their Cholesky factors of all operator rows for the reference's 81-point regularizer
+    grid (PDEs/step3_estimate.py:22: logspace(-16, 4, 81)) in one call; operator rows of length d = 45 (r = 8 quadratic)."""
+    G, n = 8, 4096
+    rng = np.random.default_rng(5)
+    regs = np.logspace(-16, 4, nreg)
+    W, where = None, "resident in HBM from the preceding lstsq_weights call"
+    D = rng.standard_normal((n, d))
+    rhs = rng.standard_normal((G, n))
+    try:
+        ctx.posterior_grid(D, rhs, regs[:2])                 # warm-up / allocation
+    except Exception:                                        # the stack was evicted by a later call: bring own weights
+        n = 1024
+        M = rng.standard_normal((G, n, n))
+        W = np.einsum("gij,gkj->gik", M, M) / n + 0.1 * np.eye(n)
+        D, rhs, where = D[:n], rhs[:, :n], "host array (H2D inside the call)"
+        ctx.posterior_grid(D, rhs, regs[:2], sqrtW=W)
+    t0 = time.perf_counter()
+    res = ctx.posterior_grid(D, rhs, regs, sqrtW=W)
+    dt = time.perf_counter() - t0
+    return {"modes": G, "m_est": n, "row_length": d, "regularizers": nreg, "host_call_seconds": dt,
+            "not_positive_definite": int(res["status"].sum()), "candidates_per_s": nreg / dt, "weights": where}
 
 
 def fit_reference_configs(ctx):

@@ -410,7 +410,7 @@ class Context:
 
     def posterior_grid(self, lhs, rhs, regularizers, sqrtW=None, want_chol=True):
         """Step-3 posterior assembly for a grid of regularizers (PDEs/step3_estimate.py:75-95 for every candidate of
-        :131-146): per GP g and regularizer k the posterior mean of the operator row, the Cholesky factor of its
+        :131-148): per GP g and regularizer k the posterior mean of the operator row, the Cholesky factor of its
         precision ``(sqrtW_g D)^T (sqrtW_g D) + reg_k^2 I`` and whether that precision is positive definite.
         sqrtW=None: the weight matrices resident on the device since the last lstsq_weights / sqrtw call.
         -> dict(means (K, G, d), chol (K, G, d, d) | None, gram (G, d, d), proj (G, d), status (K, G))."""

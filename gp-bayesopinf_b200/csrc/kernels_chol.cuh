@@ -159,14 +159,15 @@ __device__ __forceinline__ double fast_rcp(double d) {
 // __syncwarp per step, no CTA-wide barrier (the all-threads version this replaces spent ~21 000 cycles per block on
 // its 32 barriers).  The 32 square roots are taken once at the end.
 // rowp: this lane's row (first of the block's 32 columns); dinv_lane receives 1 / L_rr.  Returns (warp-uniformly)
-// whether a pivot was <= 0 (the pivot is then replaced by 1).  Not inlined: its 32-double register row must not
+// whether a pivot was <= 0 (the pivot is then replaced by 1).  nv: number of leading rows that are not identity padding.
+// Not inlined: its 32-double register row must not
 // inflate the register allocation of the DMMA kernels that call it.
 #ifndef GPBO_CHOL32_INLINE
 #define GPBO_CHOL32_ATTR __noinline__
 #else
 #define GPBO_CHOL32_ATTR __forceinline__
 #endif
-__device__ GPBO_CHOL32_ATTR bool warp_chol32(double* rowp, double* dinv_lane) {
+__device__ GPBO_CHOL32_ATTR bool warp_chol32(double* rowp, double* dinv_lane, int nv) {
     __shared__ __align__(16) double colbuf[2][32];
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -181,6 +182,9 @@ __device__ GPBO_CHOL32_ATTR bool warp_chol32(double* rowp, double* dinv_lane) {
     bool bad = false;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
+        // rows / columns >= nv are identity padding (the reference's sizes m = 10 ... 200 rarely fill the last block):
+        // their pivots are 1 and their multipliers 0, so the remaining steps change nothing (warp-uniform exit)
+        if (j >= nv) break;
         double d = __shfl_sync(FULL, a[j], j);
         double* col = colbuf[j & 1];
         col[lane] = a[j];
@@ -214,10 +218,10 @@ __device__ GPBO_CHOL32_ATTR bool warp_chol32(double* rowp, double* dinv_lane) {
 #ifndef GPBO_CHOL32_ALLTHREADS
 // Cholesky of the 32x32 block at P[o..o+32)^2 (lower part, in place, row stride LDP) by warp 0; dinv[o+i] = 1 / L_ii.
 // `flag` = one double of scratch.  Ends with __syncthreads(); returns (uniformly) whether a pivot was <= 0.
-__device__ __forceinline__ bool chol32_block(double* P, int o, double* dinv, double* flag) {
+__device__ __forceinline__ bool chol32_block(double* P, int o, double* dinv, double* flag, int nv = 32) {
     if (threadIdx.x < 32) {
         const int lane = threadIdx.x;
-        const bool bad = warp_chol32(P + (o + lane) * LDP + o, dinv + o + lane);
+        const bool bad = warp_chol32(P + (o + lane) * LDP + o, dinv + o + lane, nv);
         if (lane == 0) *flag = bad ? 1.0 : 0.0;
     }
     __syncthreads();
@@ -226,7 +230,7 @@ __device__ __forceinline__ bool chol32_block(double* P, int o, double* dinv, dou
 
 #else
 // Variant kept for A/B measurements (-DGPBO_CHOL32_ALLTHREADS): all 256 threads, one CTA barrier per pivot step.
-__device__ __forceinline__ bool chol32_block(double* P, int o, double* dinv, double* rsv) {
+__device__ __forceinline__ bool chol32_block(double* P, int o, double* dinv, double* rsv, int /*nv*/ = 32) {
     const int tid = threadIdx.x;
     const int r = tid >> 3, c8 = tid & 7;                 // row of the block, column class
     double* Pr = P + (o + r) * LDP + o;
@@ -288,7 +292,7 @@ __device__ __forceinline__ bool potf2_trtri_smem(double* P, double* scratch, dou
     }
     for (int kb = 0; kb < nvb; ++kb) {
         const int o = kb * PB;
-        bad |= chol32_block(P, o, dinv, rsv);
+        bad |= chol32_block(P, o, dinv, rsv, min(PB, nv - o));
         const int R0 = o + PB, n = nact - R0;
         if (n <= 0) break;
         // (2) panel by forward substitution, one thread per row:  X L_kk^T = A  (row in registers, L_kk broadcast)

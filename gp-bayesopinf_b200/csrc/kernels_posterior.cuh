@@ -4,7 +4,7 @@
 // For every mode i (weights sqrtW_i from compute_lstsq_matrices, shared data matrix D, right-hand side z_i):
 //     A_i = sqrtW_i D,  b_i = sqrtW_i z_i                      codebase/wlstsq.py:183-188   (weighted_products_kernel)
 //     G_i = A_i^T A_i,  g_i = A_i^T b_i                                                      (gram_kernel)
-// and for every regulariser lambda_k of the grid (step3_estimate.py:131-146 walks 81 of them, one solve each):
+// and for every regulariser lambda_k of the grid (step3_estimate.py:131-148 walks 81 of them, one solve each):
 //     precision  P_ik = G_i + lambda_k^2 I                     step3_estimate.py:86-90
 //     mean       mu_ik = argmin |A_i o - b_i|^2 + lambda_k^2 |o|^2 = P_ik^-1 g_i            step3_estimate.py:78-79
 //     Cholesky   P_ik = C C^T -- what bayes.BayesianROM builds through scipy.stats.Covariance.from_precision

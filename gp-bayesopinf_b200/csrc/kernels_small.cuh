@@ -105,10 +105,10 @@ __device__ __forceinline__ void small_block_sum(double (&v)[NV], double* red, do
 // Cholesky of the 32 x 32 diagonal block at (o, o) of the packed matrix by warp 0 (warp_chol32, kernels_chol.cuh:
 // registers + shuffles, no barrier inside).  dinv[o + i] = 1 / L_ii.  flag: one double of scratch.  Ends with
 // __syncthreads(); returns (uniformly) whether a pivot was <= 0.  flag: 33 doubles of scratch.
-__device__ __forceinline__ bool small_chol32(double* L, int o, double* dinv, double* flag) {
+__device__ __forceinline__ bool small_chol32(double* L, int o, double* dinv, double* flag, int nv = 32) {
     if (threadIdx.x < 32) {
         const int lane = threadIdx.x;
-        const bool bad = warp_chol32(L + tri(o + lane) + o, dinv + o + lane);
+        const bool bad = warp_chol32(L + tri(o + lane) + o, dinv + o + lane, nv);
         if (lane == 0) *flag = bad ? 1.0 : 0.0;
     }
     __syncthreads();
@@ -116,7 +116,7 @@ __device__ __forceinline__ bool small_chol32(double* L, int o, double* dinv, dou
 }
 #else
 // Variant kept for A/B measurements (-DGPBO_CHOL32_ALLTHREADS): all threads of the CTA, one barrier per pivot step.
-__device__ __forceinline__ bool small_chol32(double* L, int o, double* dinv, double* rsv) {
+__device__ __forceinline__ bool small_chol32(double* L, int o, double* dinv, double* rsv, int /*nv*/ = 32) {
     const int NT = blockDim.x;
     const int TPR = NT / SB;
     const int tid = threadIdx.x;
@@ -206,7 +206,7 @@ __device__ void small_eval(const SmallProblem& pr, int gp, double th0, double th
     bool bad = false;
     for (int kb = 0; kb < nblk; ++kb) {
         const int o = kb * SB;
-        bad |= small_chol32(L, o, dinv, red);
+        bad |= small_chol32(L, o, dinv, red, min(SB, m - o));
         small_mark(clk, 1);
         const int R0 = o + SB, nb = n - R0;
         if (nb <= 0) break;

@@ -1,6 +1,6 @@
 """Posterior assembly of step 3 on the GPU -- the linear algebra of ``PDEs/step3_estimate.py:75-95``
 (``get_bayesian_model(reg)``: posterior mean of every operator row, precision ``(sqrtW_i D)^T (sqrtW_i D) + reg^2 I``)
-evaluated for a whole grid of regularizers in one call (the grid search of ``:131-146`` tries 81 of them, each a
+evaluated for a whole grid of regularizers in one call (the grid search of ``:131-148`` tries 81 of them, each a
 separate solve on the CPU).
 
 What this module does NOT do is the rest of the grid search: for every candidate the reference draws operator samples

@@ -191,7 +191,7 @@ int gpbo_weighted_products_host(gpbo_ctx* ctx, const double* sqrtw, int G, int n
                                 const double* rhs, double* out_lhs, double* out_rhs);
 
 /* Posterior assembly of step 3 for a grid of regularizers (the linear algebra of
- * PDEs/step3_estimate.py:75-95 = get_bayesian_model(reg), for all candidates of the grid search :131-146 at once).
+ * PDEs/step3_estimate.py:75-95 = get_bayesian_model(reg), for all candidates of the grid search :131-148 at once).
  * For every GP / mode g and every regularizer regs[k]:
  *   A_g = sqrtW[g] @ lhs, b_g = sqrtW[g] @ rhs[g]          (codebase/wlstsq.py:183-188)
  *   gram[g] = A_g^T A_g, proj[g] = A_g^T b_g;  precision P = gram[g] + regs[k]^2 I      (step3_estimate.py:86-90)

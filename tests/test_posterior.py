@@ -68,22 +68,30 @@ def test_posterior_grid_real_moments(ctx, name):
     rc = C.shape[0]
     W = reference_sqrtW(C, eta)
     D = quadratic_data_matrix(Q)
-    regs = np.logspace(-4, 4, 17)
+    # The quadratic data matrix of the SEIRD states is rank deficient (S + E + I + R + D = 1: cond(D) = 3e15), so its
+    # grid starts where the regularised problem is defined to double precision (cond(P) <= 2e13); Euler: cond(A) = 1.6e3.
+    well = name.startswith("euler")
+    regs = np.logspace(-4, 4, 17) if well else np.logspace(-2, 4, 13)
     ref = orc.np_posterior_grid(W, D, Z[:rc], regs)
     got = ctx.posterior_grid(D, Z[:rc], regs, sqrtW=W)
     assert np.array_equal(got["status"], ref["status"]) and not got["status"].any()
     e_gram, e_proj = rel(got["gram"], ref["gram"]), rel(got["proj"], ref["proj"])
-    e_chol = max(rel(got["chol"][k], ref["chol"][k]) for k in range(regs.size))
     e_mean = max(rel(got["means"][k, i], ref["means"][k, i]) for k in range(regs.size) for i in range(rc))
-    for key, v in (("gram", e_gram), ("proj", e_proj), ("chol", e_chol), ("mean", e_mean)):
+    # Cholesky factors: backward error (C C^T against the precision of step3_estimate.py:86-90) everywhere; element-wise
+    # against LAPACK's factor where the factor itself is well conditioned
+    eye = np.eye(D.shape[1])
+    e_chol_back = max(rel(got["chol"][k, i] @ got["chol"][k, i].T, got["gram"][i] + regs[k] ** 2 * eye)
+                      for k in range(regs.size) for i in range(rc))
+    e_chol = max(rel(got["chol"][k], ref["chol"][k]) for k in range(regs.size))
+    for key, v in (("gram", e_gram), ("proj", e_proj), ("chol_backward", e_chol_back), ("mean", e_mean)):
         record(f"posterior_grid_{key}_rel[{name}]", v)
-    assert e_gram <= 1e-10 and e_proj <= 1e-10 and e_chol <= 1e-10 and e_mean <= 1e-9
-    # strict upper part of the factor is zero, the factor reproduces the precision of step3_estimate.py:86-90
-    k = 5
-    for i in range(rc):
-        Cf = got["chol"][k, i]
-        assert np.all(np.triu(Cf, 1) == 0.0)
-        assert rel(Cf @ Cf.T, got["gram"][i] + regs[k] ** 2 * np.eye(D.shape[1])) <= 1e-12
+    assert e_gram <= 1e-10 and e_proj <= 1e-10 and e_chol_back <= 1e-13 and e_mean <= 1e-9
+    if well:
+        record(f"posterior_grid_chol_rel[{name}]", e_chol)
+        assert e_chol <= 1e-10
+    for k in (0, regs.size - 1):
+        for i in range(rc):
+            assert np.all(np.triu(got["chol"][k, i], 1) == 0.0)      # strict upper part of the factor is zero
 
 
 @pytest.mark.gpu
