@@ -57,6 +57,30 @@ def test_oracle_posterior_grid_satisfies_its_defining_equations():
     assert np.all(o0["status"][0] == 1) and np.all(o0["status"][1] == 0)
 
 
+def test_posterior_grid_host_mirror_logic():
+    """PosteriorGrid (the host object the reference-side loop reads) on the oracle's numbers: precisions as in
+    step3_estimate.py:84-90, the not-positive-definite flag, draws distributed as N(mean, precision^-1)."""
+    from gpbo_pkg import pkg
+
+    rng = np.random.default_rng(4)
+    r, n, d = 2, 40, 5
+    M = rng.standard_normal((r, n, n))
+    W = np.array([m @ m.T / n + 0.2 * np.eye(n) for m in M])
+    D, Z = rng.standard_normal((n, d)), rng.standard_normal((r, n))
+    regs = np.array([0.0, 2.0])
+    pg = pkg.step3_posterior.PosteriorGrid(regs, orc.np_posterior_grid(W, D, Z, regs))
+    A0 = W[0] @ D
+    assert rel(pg.precisions(1)[0], A0.T @ A0 + 4.0 * np.eye(d)) <= 1e-13 and pg.is_spd(0) and pg.is_spd(1)
+    draws = np.array([pg.draw(1, rng)[0] for _ in range(4000)])
+    cov = np.linalg.inv(pg.precisions(1)[0])
+    assert np.abs(draws.mean(0) - pg.means[1, 0]).max() <= 5 * np.sqrt(cov.diagonal().max() / 4000)
+    assert rel(np.cov(draws.T), cov) <= 0.15
+    pg.status[0, 1] = 1
+    assert not pg.is_spd(0)
+    with pytest.raises(np.linalg.LinAlgError):
+        pg.draw(0, rng)
+
+
 # ---------------------------------------------------------------- CUDA path
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["euler_006_200_03_400_6", "seird_090_090_10_360"])
