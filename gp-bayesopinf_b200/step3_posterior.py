@@ -67,6 +67,8 @@ def posterior_grid(gps_or_sqrtW, data_matrix, rhs, regularizers, *, ctx=None, wa
     w = None
     if gps_or_sqrtW is not None:
         if isinstance(gps_or_sqrtW, (list, tuple)) and hasattr(gps_or_sqrtW[0], "sqrtW"):
+            if any(getattr(gp, "sqrtW", None) is None for gp in gps_or_sqrtW):
+                raise ValueError("a GP has no sqrtW (fit with want_sqrtW=True, or gather_cov=True on every rank)")
             w = np.array([gp.sqrtW for gp in gps_or_sqrtW])
         else:
             w = np.asarray(gps_or_sqrtW, dtype=np.float64)

@@ -148,6 +148,29 @@ def test_posterior_grid_resident_weights_and_host_mirror(ctx):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("n,d", [(3200, 128), (50, 1), (97, 17)])
+def test_posterior_grid_sizes(ctx, n, d):
+    """Largest supported operator row (d = 128: 135 KB of dynamic shared memory) at the reference's m' = 3200, a single
+    unknown, and sizes off every tile."""
+    if ctx.path != "blocked":
+        pytest.skip("path independent")
+    rng = np.random.default_rng(n + d)
+    r = 2
+    # weights with the structure of (C + eta I)^(-1/2): smooth SPD matrices, built without an n^3 eigen-decomposition
+    t = np.linspace(0, 1, n)
+    W = np.array([np.exp(-0.5 * ((t[:, None] - t[None, :]) / ell) ** 2) + 0.5 * np.eye(n) for ell in (0.05, 0.2)])
+    D, Z = rng.standard_normal((n, d)), rng.standard_normal((r, n))
+    regs = np.array([1e-3, 1.0, 30.0])
+    got, ref = ctx.posterior_grid(D, Z, regs, sqrtW=W), orc.np_posterior_grid(W, D, Z, regs)
+    assert not got["status"].any() and not ref["status"].any()
+    assert rel(got["gram"], ref["gram"]) <= 1e-11 and rel(got["proj"], ref["proj"]) <= 1e-11
+    e_mean = max(rel(got["means"][k, i], ref["means"][k, i]) for k in range(3) for i in range(r))
+    e_chol = max(rel(got["chol"][k, i], ref["chol"][k, i]) for k in range(3) for i in range(r))
+    record(f"posterior_grid_mean_rel[n={n}, d={d}]", e_mean)
+    assert e_mean <= 1e-9 and e_chol <= 1e-9
+
+
+@pytest.mark.gpu
 def test_posterior_grid_not_positive_definite_and_errors(ctx):
     if ctx.path != "blocked":
         pytest.skip("path independent")
