@@ -424,9 +424,12 @@ int eval_wave(gpbo_ctx* c, cudaStream_t s, const double* t_dev, const double* yp
     // Few pairs in flight: the factorisation is a chain of T dependent (partials -> diagonal block -> panel) steps that
     // leaves most SMs idle, and row i of W = L^-1 needs only what exists once diagonal block i is done -- so the inverse
     // rows run on a side stream, each behind the event of "its" diagonal block, in the shadow of the chain (single pair,
-    // m = 4096: 9.9 -> ~7 ms per evaluation; the optimiser's tail is a sequence of such evaluations).  With many pairs
+    // m = 4096: 8.9 -> 7.4 ms per evaluation; the optimiser's tail is a sequence of such evaluations).  With many pairs
     // every launch fills the GPU and the two streams would only compete, so the rows stay on the main stream.
-    static const int overlap_max = std::getenv("GPBO_OVERLAP_MAX") ? std::atoi(std::getenv("GPBO_OVERLAP_MAX")) : 48;
+    // Measured gain at m = 4096: 17 % at 1 pair, 13 % at 8, 6 % at 56, 3 % at 96, 2 % at 148 (one diagonal-block CTA per
+    // SM); the default limit is the SM count (profiles/r02d_tail_overlap.txt).
+    static const int overlap_env = std::getenv("GPBO_OVERLAP_MAX") ? std::atoi(std::getenv("GPBO_OVERLAP_MAX")) : -1;
+    const int overlap_max = overlap_env >= 0 ? overlap_env : sm_count(c);
     const bool overlap = with_grad && nb <= overlap_max && a.T >= 4;
     if (overlap) {
         if (!c->side) {

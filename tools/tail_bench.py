@@ -16,7 +16,8 @@ ctx = pkg.default_context(0)
 T, Y, theta, gp_of = pkg.workload.eval_workload(4, m, 32)
 ctx.upload_problem(T, Y)
 out = {"m": m, "overlap_max": os.environ.get("GPBO_OVERLAP_MAX", "default"), "ms_per_eval_call": {}}
-for B in (1, 2, 4, 8, 16, 32, 48, 64, 96):
+BATCHES = tuple(int(x) for x in os.environ.get("TAIL_BATCHES", "1,2,4,8,16,32,48,64,96").split(","))
+for B in BATCHES:
     ctx.lml_grad_resident(theta[:B], gp_of[:B])
     t0 = time.perf_counter()
     for _ in range(5):
